@@ -1,0 +1,165 @@
+/* liodom_b200 — C ABI of the B200-native LiODOM hot path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA, torch, PCL, Eigen or ROS types cross this
+ * boundary.  The reference (emiliofidalgo/liodom) has no FFI layer: its boundary is the
+ * C++ class surface that src/liodom_node.cc and src/liodom_mapping_node.cc call.  Each
+ * entry point below names the reference code it replaces; include/liodom/ holds the
+ * C++ facade (same class names) that calls these, and INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative LIODOM_E_* code otherwise and never
+ *    throws; liodom_last_error() gives the message (the reference logs and continues,
+ *    SURVEY.md §8(b) "Error conventions").
+ *  - points are float32 x,y,z,intensity at the start of each record; `stride_bytes` is
+ *    the record size (32 for pcl::PointXYZI, include/liodom/defs.h:35; 16 for packed).
+ *  - poses are row-major 4x4 double, world_from_sensor (Eigen::Isometry3d::matrix()).
+ *  - a context owns `batch` independent sequences ("lanes"); the reference's single
+ *    stream is lane 0 of a batch-1 context.  One context = one worker thread + one CUDA
+ *    stream; no re-entrancy (SURVEY.md §8(b) "Threading").
+ *  - there is no CPU fallback: if no CUDA device is usable, creation fails.
+ */
+#ifndef LIODOM_B200_H
+#define LIODOM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIODOM_OK 0
+#define LIODOM_E_INVALID -1   /* bad argument / unsupported scan_lines or lidar_type */
+#define LIODOM_E_CUDA -2      /* CUDA runtime error (message has the call site) */
+#define LIODOM_E_CAPACITY -3  /* input larger than the capacities given at creation */
+#define LIODOM_E_NODEVICE -4  /* no usable sm_100 device */
+
+/* Numeric fields of liodom::Params (include/liodom/params.h:33-52; defaults
+ * src/params.cc:40-108) plus capacities. */
+typedef struct liodom_params {
+  double min_range;       /* 3.0 */
+  double max_range;       /* 75.0 */
+  int lidar_type;         /* 0 Velodyne (ring from elevation), 1 Ouster (ring = row) */
+  int scan_lines;         /* 64 (16/32/64 for Velodyne; any <=128 for Ouster) */
+  int scan_regions;       /* 8 */
+  int edges_per_region;   /* 10 */
+  int prev_frames;        /* 5; launch files use 15 (local_map_size_) */
+  int filter_local_map;   /* 0 */
+  int mapping;            /* 0 */
+  int max_points;         /* capacity: points per scan (default 262144) */
+  int max_received_map;   /* capacity: points of the received local map (mapping=1) */
+} liodom_params;
+
+typedef struct liodom_ctx liodom_ctx;
+
+void liodom_default_params(liodom_params* p);
+
+/* Replaces the FeatureExtractor / LaserOdometer constructors
+ * (src/feature_extractor.cc:24-37, src/laser_odometry.cc:71-95). */
+int liodom_ctx_create(const liodom_params* p, int batch, int device, liodom_ctx** out);
+void liodom_ctx_destroy(liodom_ctx* ctx);
+const char* liodom_last_error(const liodom_ctx* ctx); /* ctx may be NULL (creation errors) */
+int liodom_max_edges(const liodom_ctx* ctx);          /* scan_lines*scan_regions*(edges_per_region+1) */
+void* liodom_stream(const liodom_ctx* ctx);           /* cudaStream_t of the context */
+int liodom_sync(liodom_ctx* ctx);
+
+/* ---- FeatureExtractor ------------------------------------------------------------ */
+
+/* splitPointCloud + isValidPoint (src/feature_extractor.cc:84-179), exposed for parity
+ * tests.  Host buffers; any output may be NULL.
+ *  ring_of_point[n]  ring id or -1;  rings_xyzi[4*n] ring-major stable compaction;
+ *  ring_offsets[scan_lines+1];  src_index[n] input index of each compacted point.
+ *  n_ambiguous: points whose ring bin is within 1e-9 of a boundary (GPU atan vs libm). */
+int liodom_split(liodom_ctx* ctx, int lane, const void* pts, int n, int stride_bytes,
+                 int width, int height, int32_t* ring_of_point, float* rings_xyzi,
+                 int32_t* ring_offsets, int32_t* src_index, int* n_valid, int* n_ambiguous);
+
+/* Body of FeatureExtractor::operator() (src/feature_extractor.cc:52-59): split +
+ * extractFeatures + extractFeaturesFromRegion.  Host in, host out.
+ *  edges_xyzi[4*liodom_max_edges()], emitted in (ring, region, pick) order.
+ *  Optional debug outputs: edge_ring/edge_idx (ring id and index within the ring),
+ *  keys[n_valid] smoothness of every ring-major point (NaN where not evaluated). */
+int liodom_extract(liodom_ctx* ctx, int lane, const void* pts, int n, int stride_bytes,
+                   int width, int height, float* edges_xyzi, int* n_edges,
+                   int32_t* edge_ring, int32_t* edge_idx, double* keys);
+
+/* ---- LocalMapManager (src/laser_odometry.cc:24-69) -------------------------------- */
+int liodom_lmap_add(liodom_ctx* ctx, int lane, const float* xyzi, int n);
+int liodom_lmap_get(liodom_ctx* ctx, int lane, float* xyzi, int cap, int* n_points, int* n_frames);
+int liodom_lmap_set_max_frames(liodom_ctx* ctx, int lane, int max_frames);
+int liodom_lmap_clear(liodom_ctx* ctx, int lane);
+/* SharedData::setLocalMap (src/shared_data.cc:91-96): received local map, mapping=1. */
+int liodom_set_received_map(liodom_ctx* ctx, int lane, const float* xyzi, int n);
+
+/* ---- LaserOdometer ---------------------------------------------------------------- */
+int liodom_odom_reset(liodom_ctx* ctx, int lane);
+int liodom_odom_set_pose(liodom_ctx* ctx, int lane, const double* odom16, const double* prev_odom16);
+int liodom_odom_get_pose(liodom_ctx* ctx, int lane, double* odom16, double* prev_odom16);
+
+typedef struct liodom_solve_summary {
+  int iterations;
+  int successful_steps;
+  int termination;  /* 0 max-iter, 1 gradient tol, 2 parameter tol, 3 function tol, 4 no residuals, 5 failure */
+  int num_residual_blocks;
+  int cost_evals, jac_evals;
+  double initial_cost, final_cost;
+} liodom_solve_summary;
+
+typedef struct liodom_frame_diag {
+  int n_edges;
+  int n_map[2];
+  int n_matches[2];
+  liodom_solve_summary solve[2];
+  double pred_pose[16];
+} liodom_frame_diag;
+
+/* addEdgeConstraints up to the residual-block list (src/laser_odometry.cc:300-361)
+ * against the lane's current window (+ received map when mapping=1), for parity tests.
+ * Per edge: knn_idx[5]/knn_d2[5] (valid when gate bit0 set), gate (bit0: d2[4] < 1.0,
+ * bit1: lambda2 > 3*lambda1), eig[3] ascending, q_world[4] transformed edge. */
+int liodom_associate(liodom_ctx* ctx, int lane, const float* edges_xyzi, int n_edges,
+                     const double* pose16, int32_t* knn_idx, float* knn_d2, uint8_t* gate,
+                     double* eig, float* q_world, int* n_map);
+
+/* One ceres::Solve of src/laser_odometry.cc:201-218 on given residual blocks
+ * (cab: n x 9 doubles c,a,b).  q = (x,y,z,w), t in/out. */
+int liodom_solve(liodom_ctx* ctx, int lane, const double* cab, int n, double* q4, double* t3,
+                 liodom_solve_summary* summary);
+
+/* One popFeatures() iteration of LaserOdometer::operator() (src/laser_odometry.cc:108-235):
+ * first frame seeds the window; afterwards predict, 2 x {associate, solve}, window update. */
+int liodom_register(liodom_ctx* ctx, int lane, const float* edges_xyzi, int n_edges,
+                    double* pose16_out, liodom_frame_diag* diag);
+
+/* ---- whole hot path, batched -------------------------------------------------------- */
+
+/* extract + register for every lane in one enqueue.  pts[l] / n[l]: scan of lane l
+ * (all with the same stride/width/height).  `on_device` != 0: pts[l] are device pointers
+ * (inputs resident in HBM); else host pointers staged through pinned memory.
+ * Asynchronous: returns after enqueueing; results are fetched with liodom_scan_results
+ * (which synchronises).  Steps may be pipelined: up to 2 scans in flight. */
+int liodom_scan_batch(liodom_ctx* ctx, const void* const* pts, const int* n, int stride_bytes,
+                      int width, int height, int on_device);
+/* poses16_out[batch*16], n_edges_out[batch] (either may be NULL) of the last enqueued scan. */
+int liodom_scan_results(liodom_ctx* ctx, double* poses16_out, int* n_edges_out);
+/* Edges of the last scan of a lane (device -> host). */
+int liodom_scan_edges(liodom_ctx* ctx, int lane, float* edges_xyzi, int cap, int* n_edges);
+/* Number of kernel launches enqueued by this context so far (bench gpu_launches). */
+long long liodom_launch_count(const liodom_ctx* ctx);
+
+/* ---- Map (src/map.cc:70-189, include/liodom/map.h:94-116) --------------------------- */
+typedef struct liodom_map liodom_map;
+int liodom_map_create(double voxel_xysize, double voxel_zsize, double resolution, int device,
+                      int max_points, liodom_map** out);
+void liodom_map_destroy(liodom_map* m);
+const char* liodom_map_last_error(const liodom_map* m);
+int liodom_map_update(liodom_map* m, const float* pts_xyzi, int n, const double* pose16);
+int liodom_map_size(liodom_map* m, int* n_points, int* n_cells);
+int liodom_map_get(liodom_map* m, float* xyzi, int cap, int* n_points);
+int liodom_map_get_local(liodom_map* m, const double* pose16, int cells_xy, int cells_z,
+                         float* xyzi, int cap, int* n_points);
+int liodom_map_cells(liodom_map* m, int32_t* keys3, int32_t* counts, int cap, int* n_cells);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIODOM_B200_H */

@@ -1,0 +1,155 @@
+// Shared device-side layouts and launch prototypes of the liodom_b200 hot path.
+//
+// HBM layout (per context, B = batch lanes; everything is [lane]-major):
+//   scan_in      B x Ncap x stride      staged input scan (host path) or caller memory
+//   ring_id      B x Ncap u8            ring of each input point (255 = rejected)
+//   chunk_hist   B x chunks x L i32     per-2048-point-chunk ring histogram
+//   rings        B x Ncap float4        ring-major stable compaction of the scan
+//   ring_off     B x (L+1) i32
+//   slots        B x Ecap float4        edges in fixed (ring, region, pick) slots
+//   edges        B x Ecap float4        compacted edges (sensor frame)
+//   win          B x S x Ecap float4    sliding window slabs (world frame), S = prev_frames+1
+//   sorted       B x Mcap float4        window points bucketed by 1 m voxel (w = logical index)
+//   htab/hcnt/hstart  B x Hcap          open-addressing voxel hash (generation tagged)
+//   blocks       B x Ecap x 10 f32      residual blocks {c, a, b, valid}
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace liodom {
+
+constexpr int kChunk = 2048;        // points per split chunk (256 threads x 8)
+constexpr int kMaxLines = 128;      // scan_lines upper bound
+constexpr int kMaxSlots = 64;       // window slabs upper bound (prev_frames + 1)
+constexpr int kRingSmemCap = 6144;  // ring points kept in shared memory by k_extract
+constexpr unsigned kGenBits = 12;   // hash generation tag width
+constexpr unsigned kCntBits = 20;
+
+struct DevParams {
+  double min_range, max_range;
+  int lidar_type, scan_lines, scan_regions, edges_per_region;
+  int prev_frames, filter_local_map, mapping;
+  int Ncap, Ecap, Mcap, Hcap, Rcap;  // Rcap: received-map capacity
+  int slots;                         // window slabs allocated
+  int chunks;                        // ceil(Ncap / kChunk)
+  int batch;
+};
+
+// Per-lane description of the scan being processed (rewritten every step).
+struct ScanDesc {
+  const void* pts;
+  int n;
+  int stride_bytes;
+  int width, height;
+};
+
+// Sliding window bookkeeping (LocalMapManager, src/laser_odometry.cc:24-69).
+struct WinState {
+  int nframes;
+  int max_frames;
+  int head;               // slab index of the oldest frame
+  int total;              // points in the window
+  int cnt[kMaxSlots];     // points per slab
+  int n_received;         // received local map points (mapping mode)
+  unsigned gen;           // hash generation of the current build
+  int hash_points;        // points inserted in the current hash build
+  int bump;               // bucket allocator
+  int pad;
+};
+
+// LaserOdometer state (src/laser_odometry.cc: odom_, prev_odom_, param_q, param_t, init_).
+struct OdomState {
+  double odom[12];        // row-major 3x4
+  double prev[12];
+  double q[4];            // x,y,z,w
+  double t[3];
+  int init;
+  int frame;
+  int n_edges;
+  int n_valid;            // valid points of the last split
+  int n_ambiguous;
+  int pad;
+};
+
+struct SolveSummaryDev {
+  int iterations, successful_steps, termination, num_residual_blocks, cost_evals, jac_evals;
+  double initial_cost, final_cost;
+};
+
+struct FrameDiagDev {
+  int n_edges;
+  int n_map[2];
+  int n_matches[2];
+  int pad;
+  SolveSummaryDev solve[2];
+  double pred_pose[16];
+};
+
+// Everything the kernels need, passed by value (fits the 4 KB parameter space).
+struct DevBuffers {
+  DevParams p;
+  ScanDesc* scan;          // [B]
+  uint8_t* ring_id;        // [B][Ncap]
+  int* chunk_hist;         // [B][chunks][L]
+  int* chunk_base;         // [B][chunks][L]
+  int* chunk_amb;          // [B][chunks] ring-bin decisions within 1e-9 of a boundary
+  float4* rings;           // [B][Ncap]
+  int* src_index;          // [B][Ncap] (debug) or null
+  int* ring_off;           // [B][L+1]
+  double* keys;            // [B][Ncap] smoothness (debug output / long-ring path)
+  unsigned* pick_bits;     // [B][2][Ncap/32 + kMaxLines + 2] picked bitmaps of the long-ring path
+  float4* slots;           // [B][Ecap]
+  int* slot_idx;           // [B][Ecap] index within ring of each slot pick
+  int* region_cnt;         // [B][L*R]
+  float4* edges;           // [B][Ecap]
+  int* edge_ring;          // [B][Ecap]
+  int* edge_idx;           // [B][Ecap]
+  float4* win;             // [B][slots][Ecap]
+  float4* received;        // [B][Rcap]
+  WinState* wstate;        // [B]
+  OdomState* ostate;       // [B]
+  float4* sorted;          // [B][Mcap]
+  unsigned long long* htab;  // [B][Hcap]
+  unsigned* hcnt;          // [B][Hcap]
+  unsigned* hstart;        // [B][Hcap]
+  unsigned* pt_slot;       // [B][Mcap]
+  unsigned* pt_rank;       // [B][Mcap]
+  float* blocks;           // [B][Ecap][10]
+  int* knn_idx;            // [B][Ecap][5] (debug) or null
+  float* knn_d2;           // [B][Ecap][5]
+  uint8_t* gate;           // [B][Ecap]
+  double* eig;             // [B][Ecap][3]
+  float4* q_world;         // [B][Ecap]
+  FrameDiagDev* diag;      // [B]
+  double* poses_out;       // [B][16]
+};
+
+// ---- launchers (each returns the number of kernels it enqueued) ----------------------
+// Every kernel works on lanes [lane0, lane0 + nlanes).
+struct LaneRange { int lane0, nlanes; };
+int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys);
+int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane);
+int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override);
+int launch_solve(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it);
+int launch_solve_blocks(const DevBuffers& d, cudaStream_t s, int lane, const double* cab, int n, double* qt_inout,
+                        SolveSummaryDev* sum);
+int launch_window_update(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_lmap_add(const DevBuffers& d, cudaStream_t s, int lane, const float4* pts_dev, int n);
+int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out);
+int extract_ring_cap(const DevParams& p);
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_cell(int ix, int iy, int iz, unsigned gen) {
+  return ((unsigned long long)gen << 48) | ((unsigned long long)(iz & 0xFFFF) << 32) |
+         ((unsigned long long)(iy & 0xFFFF) << 16) | (unsigned long long)(ix & 0xFFFF);
+}
+__device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+  k &= 0xFFFFFFFFFFFFull;
+  k ^= k >> 23; k *= 0x2127599BF4325C37ull; k ^= k >> 47;
+  return (unsigned)k;
+}
+
+}  // namespace liodom

@@ -1,0 +1,463 @@
+// FeatureExtractor hot path on sm_100a: ring split, 11-tap curvature, per-region greedy
+// top-k with +-5 suppression (replaces src/feature_extractor.cc:84-313 of the reference).
+//
+// Compiled with -fmad=false; the float/double sequences below additionally use the
+// explicit round-to-nearest intrinsics so that no contraction can change a rounding
+// (the reference is built without -march, i.e. SSE2 without FMA, CMakeLists.txt:13).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace liodom {
+
+// ---------------------------------------------------------------------------------------
+// A1 + A2: isValidPoint + ring id (src/feature_extractor.cc:84-102, :126-151, :160-175)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_xyz(const ScanDesc& sc, int i, float& x, float& y, float& z) {
+  const char* base = reinterpret_cast<const char*>(sc.pts) + (size_t)i * sc.stride_bytes;
+  if ((sc.stride_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(sc.pts) & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base));
+    x = v.x; y = v.y; z = v.z;
+  } else {
+    const float* f = reinterpret_cast<const float*>(base);
+    x = __ldg(f); y = __ldg(f + 1); z = __ldg(f + 2);
+  }
+}
+__device__ __forceinline__ float4 load_xyzi(const ScanDesc& sc, int i) {
+  const char* base = reinterpret_cast<const char*>(sc.pts) + (size_t)i * sc.stride_bytes;
+  // pcl::PointXYZI keeps intensity in the second 16-byte half (data_c[0]); packed records at +12.
+  const int ioff = sc.stride_bytes >= 32 ? 16 : 12;
+  float4 v;
+  if ((sc.stride_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(sc.pts) & 15) == 0) {
+    v = __ldg(reinterpret_cast<const float4*>(base));
+    if (ioff != 12) v.w = __ldg(reinterpret_cast<const float*>(base + ioff));
+  } else {
+    const float* f = reinterpret_cast<const float*>(base);
+    v.x = __ldg(f); v.y = __ldg(f + 1); v.z = __ldg(f + 2);
+    v.w = sc.stride_bytes >= 16 ? __ldg(reinterpret_cast<const float*>(base + ioff)) : 0.f;
+  }
+  return v;
+}
+
+__device__ __forceinline__ bool near_int(double v) { return fabs(v - rint(v)) < 1e-9; }
+
+// Returns ring id or -1. `amb` is set when a bin decision sits within 1e-9 of a boundary
+// (device atan is <=2 ulp, libm <=1 ulp: such a point could land in the other bin).
+__device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, bool& amb) {
+  const double x = xf, y = yf, z = zf;
+  bool valid = isfinite(x) && isfinite(y) && isfinite(z);
+  const double dist = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  if (dist > p.max_range || dist < p.min_range) valid = false;
+  amb = false;
+  if (!valid) return -1;
+  if (p.lidar_type == 1) {
+    const int row = i / sc.width;
+    return row < p.scan_lines ? row : -1;
+  }
+  const double angle = __ddiv_rn(__dmul_rn(atan(__ddiv_rn(z, dist)), 180.0), 3.14159265358979323846);
+  int id = -1;
+  if (p.scan_lines == 64) {
+    double v;
+    if (angle >= -8.83) { v = __dadd_rn(__dmul_rn(__dsub_rn(2.0, angle), 3.0), 0.5); id = __double2int_rz(v); }
+    else { v = __dadd_rn(__dmul_rn(__dsub_rn(-8.83, angle), 2.0), 0.5); id = 32 + __double2int_rz(v); }
+    amb = near_int(v) || fabs(angle + 8.83) < 1e-9 || fabs(angle - 2.0) < 1e-9 || fabs(angle + 24.33) < 1e-9;
+    if (angle > 2.0 || angle < -24.33 || id > 63 || id < 0) id = -1;
+  } else if (p.scan_lines == 32) {
+    const double v = __ddiv_rn(__dmul_rn(__dadd_rn(angle, 92.0 / 3.0), 3.0), 4.0);
+    id = __double2int_rz(v); amb = near_int(v);
+    if (id > 31 || id < 0) id = -1;
+  } else if (p.scan_lines == 16) {
+    const double v = __dadd_rn(__ddiv_rn(__dadd_rn(angle, 15.0), 2.0), 0.5);
+    id = __double2int_rz(v); amb = near_int(v);
+    if (id > 15 || id < 0) id = -1;
+  }
+  return id;
+}
+
+// Pass 1: ring id per point + per-chunk histogram. grid (chunks, B), 256 threads, each warp
+// owns a contiguous 256-point segment so that (warp, round, lane) is input order.
+__global__ void __launch_bounds__(256) k_split_count(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y, chunk = blockIdx.x;
+  const ScanDesc sc = d.scan[lane_b];
+  const DevParams& p = d.p;
+  const int L = p.scan_lines;
+  __shared__ int hist[kMaxLines];
+  __shared__ int s_amb;
+  if (threadIdx.x < kMaxLines) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_amb = 0;
+  __syncthreads();
+  const int base = chunk * kChunk;
+  if (base < sc.n) {
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    uint8_t* rid = d.ring_id + (size_t)lane_b * p.Ncap;
+    int namb = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = base + w * 256 + r * 32 + ln;
+      int id = -1;
+      if (i < sc.n) {
+        float x, y, z; load_xyz(sc, i, x, y, z);
+        bool amb; id = ring_of_point(p, sc, i, x, y, z, amb);
+        namb += amb ? 1 : 0;
+        rid[i] = id < 0 ? (uint8_t)255 : (uint8_t)id;
+      }
+      const unsigned m = __match_any_sync(0xffffffffu, id);
+      if (id >= 0 && (__ffs(m) - 1) == ln) atomicAdd(&hist[id], __popc(m));
+    }
+    if (namb) atomicAdd(&s_amb, namb);
+  }
+  __syncthreads();
+  int* out = d.chunk_hist + ((size_t)lane_b * p.chunks + chunk) * L;
+  if (threadIdx.x < L) out[threadIdx.x] = hist[threadIdx.x];
+  if (threadIdx.x == 0) d.chunk_amb[(size_t)lane_b * p.chunks + chunk] = s_amb;
+}
+
+// Pass 2: exclusive scan over (ring-major, chunk) -> chunk_base, ring_off. grid B, 128 threads.
+__global__ void __launch_bounds__(kMaxLines) k_split_scan(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.x;
+  const DevParams& p = d.p;
+  const int L = p.scan_lines, r = threadIdx.x;
+  const ScanDesc sc = d.scan[lane_b];
+  const int nch = (sc.n + kChunk - 1) / kChunk;
+  __shared__ int tot[kMaxLines + 1];
+  int run = 0;
+  if (r < L) {
+    const int* h = d.chunk_hist + (size_t)lane_b * p.chunks * L + r;
+    int* b = d.chunk_base + (size_t)lane_b * p.chunks * L + r;
+    for (int c = 0; c < nch; ++c) { const int v = h[(size_t)c * L]; b[(size_t)c * L] = run; run += v; }
+    tot[r] = run;
+  }
+  __syncthreads();
+  if (r == 0) {
+    int acc = 0;
+    int* off = d.ring_off + (size_t)lane_b * (L + 1);
+    for (int k = 0; k < L; ++k) { off[k] = acc; acc += tot[k]; }
+    off[L] = acc;
+    d.ostate[lane_b].n_valid = acc;
+    int amb = 0;
+    for (int c = 0; c < nch; ++c) amb += d.chunk_amb[(size_t)lane_b * p.chunks + c];
+    d.ostate[lane_b].n_ambiguous = amb;
+  }
+}
+
+// Pass 3: stable scatter into ring-major order. grid (chunks, B), 256 threads.
+__global__ void __launch_bounds__(256) k_split_scatter(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y, chunk = blockIdx.x;
+  const ScanDesc sc = d.scan[lane_b];
+  const DevParams& p = d.p;
+  const int L = p.scan_lines;
+  const int base = chunk * kChunk;
+  if (base >= sc.n) return;
+  __shared__ int wcnt[8][kMaxLines];
+  for (int k = threadIdx.x; k < 8 * kMaxLines; k += 256) (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  const uint8_t* rid = d.ring_id + (size_t)lane_b * p.Ncap;
+  int ids[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = base + w * 256 + r * 32 + ln;
+    int id = -1;
+    if (i < sc.n) { const uint8_t v = rid[i]; id = v == 255 ? -1 : (int)v; }
+    ids[r] = id;
+    const unsigned m = __match_any_sync(0xffffffffu, id);
+    if (id >= 0 && (__ffs(m) - 1) == ln) wcnt[w][id] += __popc(m);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < L) {
+    const int r = threadIdx.x;
+    int run = d.chunk_base[((size_t)lane_b * p.chunks + chunk) * L + r] + d.ring_off[(size_t)lane_b * (L + 1) + r];
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) { const int c = wcnt[ww][r]; wcnt[ww][r] = run; run += c; }
+  }
+  __syncthreads();
+  float4* rings = d.rings + (size_t)lane_b * p.Ncap;
+  int* src = d.src_index ? d.src_index + (size_t)lane_b * p.Ncap : nullptr;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = base + w * 256 + r * 32 + ln;
+    const int id = ids[r];
+    const unsigned m = __match_any_sync(0xffffffffu, id);
+    if (id >= 0) {
+      const int pos = wcnt[w][id] + __popc(m & ((1u << ln) - 1u));
+      rings[pos] = load_xyzi(sc, i);
+      if (src) src[pos] = i;
+    }
+    __syncwarp();
+    if (id >= 0 && (__ffs(m) - 1) == ln) wcnt[w][id] += __popc(m);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// A3 + A4: curvature and greedy selection, one CTA per (ring, lane).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// 11-tap sum in float, strictly left to right, 10*x a separate float multiply
+// (src/feature_extractor.cc:196-228).
+__device__ __forceinline__ float tap11(float m5, float m4, float m3, float m2, float m1, float c,
+                                       float p1, float p2, float p3, float p4, float p5) {
+  float s = __fadd_rn(m5, m4);
+  s = __fadd_rn(s, m3); s = __fadd_rn(s, m2); s = __fadd_rn(s, m1);
+  s = __fsub_rn(s, __fmul_rn(10.0f, c));
+  s = __fadd_rn(s, p1); s = __fadd_rn(s, p2); s = __fadd_rn(s, p3); s = __fadd_rn(s, p4); s = __fadd_rn(s, p5);
+  return s;
+}
+
+// squared gap between consecutive ring points a, b (src/feature_extractor.cc:281-289):
+// float differences widened to double, then dx*dx + dy*dy + dz*dz in double.
+__device__ __forceinline__ double gap2(const float4& a, const float4& b) {
+  const double dx = (double)__fsub_rn(a.x, b.x), dy = (double)__fsub_rn(a.y, b.y), dz = (double)__fsub_rn(a.z, b.z);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+struct RingView {
+  const float4* P;    // ring points (shared or global)
+  const double* K;    // smoothness per ring index
+  unsigned* bits;     // picked bitmap over ring indices
+  int n;
+};
+
+__device__ __forceinline__ bool bit_get(const unsigned* bits, int i) { return (((const volatile unsigned*)bits)[i >> 5] >> (i & 31)) & 1u; }
+__device__ __forceinline__ void bit_set(unsigned* bits, int i) { atomicOr(&bits[i >> 5], 1u << (i & 31)); }
+
+// Mark idx and its +-5 neighbourhood (gap-limited) into `bits`, restricted to [lo, hi).
+// Executed by one full warp: lanes 0-4 test the forward gaps, lanes 8-12 the backward gaps.
+__device__ __forceinline__ void mark_pick(const RingView& rv, unsigned* bits, int idx, int lo, int hi, int ln) {
+  bool brk = false;
+  if (ln < 5) { const int l = ln + 1; brk = gap2(rv.P[idx + l], rv.P[idx + l - 1]) > 0.05; }
+  else if (ln >= 8 && ln < 13) { const int l = ln - 7; brk = gap2(rv.P[idx - l], rv.P[idx - l + 1]) > 0.05; }
+  const unsigned bm = __ballot_sync(0xffffffffu, brk);
+  const unsigned f = bm & 0x1fu, b = (bm >> 8) & 0x1fu;
+  const int nf = f ? (__ffs(f) - 1) : 5, nb = b ? (__ffs(b) - 1) : 5;  // marks before the first break
+  if (ln == 0) { if (idx >= lo && idx < hi) bit_set(bits, idx); }
+  if (ln >= 1 && ln <= nf) { const int j = idx + ln; if (j >= lo && j < hi) bit_set(bits, j); }
+  if (ln >= 9 && ln <= 8 + nb) { const int j = idx - (ln - 8); if (j >= lo && j < hi) bit_set(bits, j); }
+  __syncwarp();
+}
+
+// Greedy selection of one region by one warp: repeated warp-shuffle arg-max over the
+// not-yet-picked items under the total order (smoothness desc, index asc). Equivalent to
+// std::sort + walk of src/feature_extractor.cc:261-312 whenever the sort order is total.
+__device__ int run_region(const RingView& rv, int lo, int hi, int epr, int* picks, int ln) {
+  int np = 0;
+  for (;;) {
+    double bk = -1.0; int bi = 0x7fffffff;
+    for (int i = lo + ln; i < hi; i += 32)
+      if (!bit_get(rv.bits, i)) { const double k = rv.K[i]; if (k > bk) { bk = k; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    if (bi == 0x7fffffff) break;            // every item already picked
+    if (bk < 0.1 || np > epr) break;        // src/feature_extractor.cc:270
+    if (ln == 0) picks[np] = bi;
+    ++np;
+    mark_pick(rv, rv.bits, bi, lo, hi, ln);
+  }
+  return np;
+}
+
+__global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y, ring = blockIdx.x;
+  const int L = p.scan_lines, R = p.scan_regions, epr = p.edges_per_region, E1 = epr + 1;
+  const int* roff = d.ring_off + (size_t)lane_b * (L + 1);
+  const int off = roff[ring], n = roff[ring + 1] - off;
+  int* rcnt = d.region_cnt + ((size_t)lane_b * L + ring) * R;
+  const int tid = threadIdx.x, ln = tid & 31, w = tid >> 5;
+  if (n < R * epr + 10) {  // min_points_per_scan_ (src/params.cc:63, src/feature_extractor.cc:188)
+    for (int r = tid; r < R; r += blockDim.x) rcnt[r] = 0;
+    return;
+  }
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [points ring_cap*16][keys ring_cap*8][bits][tbits][picks R*E1][npicks R]
+  float4* sp = reinterpret_cast<float4*>(smem);
+  double* sk = reinterpret_cast<double*>(smem + (size_t)ring_cap * 16);
+  const bool in_smem = n <= ring_cap;
+  const int nwords = (n + 31) >> 5;
+  const int wcap = (ring_cap + 31) >> 5;
+  unsigned* sbits = reinterpret_cast<unsigned*>(smem + (size_t)ring_cap * 24);
+  unsigned* stbits = sbits + wcap;
+  int* picks = reinterpret_cast<int*>(stbits + wcap);
+  int* npicks = picks + R * E1;
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const float4* gp = d.rings + (size_t)lane_b * p.Ncap + off;
+  RingView rv;
+  rv.n = n;
+  if (in_smem) {
+    // TMA bulk copy of the whole ring (n*16 bytes, 16-byte aligned) into shared memory.
+    const unsigned bytes = (unsigned)n * 16u;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sp)), "l"(gp), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    for (int k = tid; k < 2 * wcap; k += blockDim.x) sbits[k] = 0u;  // overlap with the copy
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(&mbar)), "r"(0) : "memory");
+    rv.P = sp; rv.K = sk; rv.bits = sbits;
+  } else {
+    // Long ring (e.g. the 1M-point scan): points stay in global/L2, keys and bitmaps in
+    // global scratch. Bitmap words [off/32 + ring, ...) are disjoint between rings.
+    double* gk = d.keys + (size_t)lane_b * p.Ncap + off;
+    const size_t bw = (size_t)(p.Ncap >> 5) + kMaxLines + 2;
+    unsigned* gbits = d.pick_bits + (size_t)lane_b * 2 * bw + (off >> 5) + ring;
+    unsigned* gtbits = gbits + bw;
+    for (int k = tid; k < nwords; k += blockDim.x) { gbits[k] = 0u; gtbits[k] = 0u; }
+    rv.P = gp; rv.K = gk; rv.bits = gbits;
+    stbits = gtbits;
+    sk = gk;
+  }
+  // curvature
+  double* gkeys = (want_keys && d.keys) ? d.keys + (size_t)lane_b * p.Ncap + off : nullptr;
+  for (int j = 5 + tid; j < n - 5; j += blockDim.x) {
+    const float4 a0 = rv.P[j - 5], a1 = rv.P[j - 4], a2 = rv.P[j - 3], a3 = rv.P[j - 2], a4 = rv.P[j - 1];
+    const float4 c = rv.P[j];
+    const float4 b1 = rv.P[j + 1], b2 = rv.P[j + 2], b3 = rv.P[j + 3], b4 = rv.P[j + 4], b5 = rv.P[j + 5];
+    const double dx = (double)tap11(a0.x, a1.x, a2.x, a3.x, a4.x, c.x, b1.x, b2.x, b3.x, b4.x, b5.x);
+    const double dy = (double)tap11(a0.y, a1.y, a2.y, a3.y, a4.y, c.y, b1.y, b2.y, b3.y, b4.y, b5.y);
+    const double dz = (double)tap11(a0.z, a1.z, a2.z, a3.z, a4.z, c.z, b1.z, b2.z, b3.z, b4.z, b5.z);
+    const double key = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    sk[j] = key;
+    if (gkeys && in_smem) gkeys[j] = key;
+  }
+  __syncthreads();
+
+  const int total = n - 10, sector = total / R;
+  const int nw = blockDim.x >> 5;
+  // speculative pass: every region on its own, marks confined to the region
+  for (int r = w; r < R; r += nw) {
+    const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
+    const int np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
+    if (ln == 0) npicks[r] = np;
+  }
+  __syncthreads();
+  // sequential fix-up (warp 0): replay the picked_ coupling between regions of the ring
+  if (w == 0) {
+    unsigned* tb = stbits;
+    for (int r = 0; r < R; ++r) {
+      const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
+      int np = npicks[r];
+      bool clash = false;
+      for (int k = ln; k < np; k += 32) clash |= bit_get(tb, picks[r * E1 + k]);
+      if (__any_sync(0xffffffffu, clash)) {
+        // a speculative pick was already suppressed by an earlier region: rerun with the true premask
+        for (int i = (lo >> 5) + ln; i <= ((hi - 1) >> 5); i += 32) {
+          unsigned m = 0xffffffffu;
+          if (i == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+          if (i == ((hi - 1) >> 5)) m &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+          rv.bits[i] = (rv.bits[i] & ~m) | (tb[i] & m);
+        }
+        __syncwarp();
+        np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
+        if (ln == 0) npicks[r] = np;
+        __syncwarp();
+      }
+      for (int k = 0; k < np; ++k) mark_pick(rv, tb, picks[r * E1 + k], 0, n, ln);
+    }
+  }
+  __syncthreads();
+  // emit into fixed (ring, region, pick) slots
+  float4* slots = d.slots + (size_t)lane_b * p.Ecap + (size_t)ring * R * E1;
+  int* sidx = d.slot_idx + (size_t)lane_b * p.Ecap + (size_t)ring * R * E1;
+  for (int s = tid; s < R * E1; s += blockDim.x) {
+    const int r = s / E1, k = s - r * E1;
+    if (k < npicks[r]) { const int j = picks[s]; slots[s] = rv.P[j]; sidx[s] = j; }
+  }
+  for (int r = tid; r < R; r += blockDim.x) rcnt[r] = npicks[r];
+}
+
+// Compaction of the fixed slots into the contiguous edge list (ring, region, pick order).
+__global__ void __launch_bounds__(1024) k_compact(DevBuffers d, int lane0) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.x, tid = threadIdx.x;
+  const int LR = p.scan_lines * p.scan_regions, E1 = p.edges_per_region + 1;
+  extern __shared__ int base[];  // LR + 32
+  int* wsum = base + LR;
+  const int* rcnt = d.region_cnt + (size_t)lane_b * LR;
+  const int per = (LR + 1023) / 1024;
+  int local = 0;
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < LR) local += rcnt[i]; }
+  int inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
+  if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+  __syncthreads();
+  if (tid < 32) {
+    int v = wsum[tid], s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, s, o); if (tid >= o) s += u; }
+    wsum[tid] = s - v;
+    if (tid == 31) { d.ostate[lane_b].n_edges = s; d.diag[lane_b].n_edges = s; }
+  }
+  __syncthreads();
+  int run = wsum[tid >> 5] + inc - local;
+  for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < LR) { base[i] = run; run += rcnt[i]; } }
+  __syncthreads();
+  const float4* slots = d.slots + (size_t)lane_b * p.Ecap;
+  const int* sidx = d.slot_idx + (size_t)lane_b * p.Ecap;
+  float4* edges = d.edges + (size_t)lane_b * p.Ecap;
+  int* ering = d.edge_ring + (size_t)lane_b * p.Ecap;
+  int* eidx = d.edge_idx + (size_t)lane_b * p.Ecap;
+  for (int s = tid; s < LR * E1; s += 1024) {
+    const int rr = s / E1, k = s - rr * E1;
+    if (k < rcnt[rr]) {
+      const int o = base[rr] + k;
+      edges[o] = slots[s]; ering[o] = rr / p.scan_regions; eidx[o] = sidx[s];
+    }
+  }
+}
+
+static size_t extract_smem_bytes(const DevParams& p, int ring_cap) {
+  const int wcap = (ring_cap + 31) >> 5;
+  return (size_t)ring_cap * 24 + (size_t)wcap * 8 + (size_t)p.scan_regions * (p.edges_per_region + 1) * 4 + (size_t)p.scan_regions * 4 + 16;
+}
+
+int extract_ring_cap(const DevParams& p) {
+  long want = ((long)p.Ncap * 5 / 4) / p.scan_lines;
+  want = (want + 255) / 256 * 256;
+  if (want < 1024) want = 1024;
+  if (want > kRingSmemCap) want = kRingSmemCap;
+  return (int)want;
+}
+
+int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
+  const dim3 g(d.p.chunks, lr.nlanes);
+  k_split_count<<<g, 256, 0, s>>>(d, lr.lane0);
+  k_split_scan<<<lr.nlanes, kMaxLines, 0, s>>>(d, lr.lane0);
+  k_split_scatter<<<g, 256, 0, s>>>(d, lr.lane0);
+  return 3;
+}
+
+int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys) {
+  const int ring_cap = extract_ring_cap(d.p);
+  const size_t sm = extract_smem_bytes(d.p, ring_cap);
+  static size_t configured = 0;
+  if (sm > configured) {
+    cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    configured = sm;
+  }
+  k_extract<<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0);
+  const int LR = d.p.scan_lines * d.p.scan_regions;
+  k_compact<<<lr.nlanes, 1024, (LR + 32) * sizeof(int), s>>>(d, lr.lane0);
+  return 2;
+}
+
+}  // namespace liodom

@@ -1,0 +1,477 @@
+// LaserOdometer data association on sm_100a: sliding window (LocalMapManager), 1 m
+// open-addressing voxel hash, exact 5-NN, line gate and residual-block assembly
+// (replaces src/laser_odometry.cc:24-69, :148-150, :186-195, :231-235, :300-361).
+//
+// Bit-exact parts (transform, float L2 distances, centroid/scatter/eigen gate) use the
+// explicit *_rn intrinsics and the file is compiled with -fmad=false.
+#include "common.cuh"
+
+namespace liodom {
+
+// ---------------------------------------------------------------------------------------
+// window addressing
+// ---------------------------------------------------------------------------------------
+struct WinView {
+  int prefix[kMaxSlots + 1];
+  int slab[kMaxSlots];
+  int nframes, total, n_received;
+};
+
+__device__ __forceinline__ void load_win_view(const DevBuffers& d, int lane_b, WinView* v) {
+  const WinState& ws = d.wstate[lane_b];
+  int acc = 0;
+  for (int k = 0; k < ws.nframes; ++k) {
+    const int s = (ws.head + k) % d.p.slots;
+    v->slab[k] = s; v->prefix[k] = acc; acc += ws.cnt[s];
+  }
+  v->prefix[ws.nframes] = acc;
+  v->nframes = ws.nframes; v->total = acc;
+  v->n_received = d.p.mapping ? ws.n_received : 0;
+}
+
+__device__ __forceinline__ float4 win_point(const DevBuffers& d, int lane_b, const WinView& v, int i) {
+  if (i >= v.total) return d.received[(size_t)lane_b * d.p.Rcap + (i - v.total)];
+  int k = 0;
+  while (i >= v.prefix[k + 1]) ++k;
+  return d.win[((size_t)lane_b * d.p.slots + v.slab[k]) * d.p.Ecap + (i - v.prefix[k])];
+}
+
+// Called by exactly one thread after the window changed: start a new hash generation.
+__device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
+  WinState& ws = d.wstate[lane_b];
+  ws.gen = ws.gen + 1u;
+  ws.bump = 0;
+  ws.hash_points = ws.total + (d.p.mapping ? ws.n_received : 0);
+}
+
+// LocalMapManager::addPointCloud bookkeeping (src/laser_odometry.cc:34-60): the new frame
+// has just been written to slab (head + nframes) % slots with `n` points.
+__device__ __forceinline__ void win_commit(const DevBuffers& d, int lane_b, int n) {
+  WinState& ws = d.wstate[lane_b];
+  const int s = (ws.head + ws.nframes) % d.p.slots;
+  ws.cnt[s] = n; ws.total += n; ws.nframes++;
+  if (ws.nframes > ws.max_frames) {  // drop exactly one (the oldest) frame
+    ws.total -= ws.cnt[ws.head]; ws.cnt[ws.head] = 0;
+    ws.head = (ws.head + 1) % d.p.slots; ws.nframes--;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// voxel hash build: insert/count -> allocate buckets -> scatter. grid (blocks, nlanes).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  __shared__ WinView v;
+  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
+  __syncthreads();
+  const WinState& ws = d.wstate[lane_b];
+  const int npts = ws.hash_points;
+  const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+  const unsigned mask = (unsigned)d.p.Hcap - 1u;
+  unsigned long long* tab = d.htab + (size_t)lane_b * d.p.Hcap;
+  unsigned* cnt = d.hcnt + (size_t)lane_b * d.p.Hcap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    const float4 pt = win_point(d, lane_b, v, i);
+    unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
+    if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { *pslot = 0xffffffffu; continue; }  // PCL kd-tree skips these
+    const unsigned long long mine = pack_cell((int)floorf(pt.x), (int)floorf(pt.y), (int)floorf(pt.z), gen);
+    unsigned slot = hash_cell(mine) & mask;
+    bool owner = false;
+    for (;;) {
+      unsigned long long cur = ((volatile unsigned long long*)tab)[slot];
+      if (cur == mine) break;
+      if ((unsigned)(cur >> 48) != gen) {  // stale generation: free
+        const unsigned long long prev = atomicCAS(&tab[slot], cur, mine);
+        if (prev == cur) { owner = true; break; }
+        if (prev == mine) break;
+        if ((unsigned)(prev >> 48) != gen) continue;  // lost to another stale observer; retry the slot
+      }
+      slot = (slot + 1) & mask;
+    }
+    atomicMax(&cnt[slot], gen << kCntBits);
+    const unsigned rank = atomicAdd(&cnt[slot], 1u) & ((1u << kCntBits) - 1u);
+    *pslot = slot | (owner ? 0x80000000u : 0u);
+    d.pt_rank[(size_t)lane_b * d.p.Mcap + i] = rank;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  WinState& ws = d.wstate[lane_b];
+  const int npts = ws.hash_points;
+  const unsigned* cnt = d.hcnt + (size_t)lane_b * d.p.Hcap;
+  unsigned* start = d.hstart + (size_t)lane_b * d.p.Hcap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
+    if (ps != 0xffffffffu && (ps & 0x80000000u)) {
+      const unsigned slot = ps & 0x7fffffffu;
+      start[slot] = (unsigned)atomicAdd(&ws.bump, (int)(cnt[slot] & ((1u << kCntBits) - 1u)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  __shared__ WinView v;
+  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
+  __syncthreads();
+  const int npts = d.wstate[lane_b].hash_points;
+  const unsigned* start = d.hstart + (size_t)lane_b * d.p.Hcap;
+  float4* sorted = d.sorted + (size_t)lane_b * d.p.Mcap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
+    const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
+    if (ps == 0xffffffffu) continue;
+    float4 pt = win_point(d, lane_b, v, i);
+    pt.w = __int_as_float(i);
+    sorted[start[ps & 0x7fffffffu] + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
+  }
+}
+
+int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
+  const int lane0 = lr.lane0, nlanes = lr.nlanes;
+  int blocks = (d.p.Mcap + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  const dim3 g(blocks, nlanes);
+  k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
+  k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
+  k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
+  return 3;
+}
+
+// ---------------------------------------------------------------------------------------
+// prediction + initial guess (src/laser_odometry.cc:148-150, :186-195). grid B, 32 threads.
+// ---------------------------------------------------------------------------------------
+__device__ void iso_mul(const double* A, const double* B, double* C) {  // row-major 3x4, implicit last row
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      C[i * 4 + j] = __dadd_rn(__dadd_rn(__dmul_rn(A[i * 4 + 0], B[0 * 4 + j]), __dmul_rn(A[i * 4 + 1], B[1 * 4 + j])), __dmul_rn(A[i * 4 + 2], B[2 * 4 + j]));
+    C[i * 4 + 3] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(A[i * 4 + 0], B[3]), __dmul_rn(A[i * 4 + 1], B[7])), __dmul_rn(A[i * 4 + 2], B[11])), A[i * 4 + 3]);
+  }
+}
+__device__ void iso_inverse(const double* A, double* C) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i * 4 + j] = A[j * 4 + i];
+  for (int i = 0; i < 3; ++i)
+    C[i * 4 + 3] = __dadd_rn(__dadd_rn(__dmul_rn(-C[i * 4 + 0], A[3]), __dmul_rn(-C[i * 4 + 1], A[7])), __dmul_rn(-C[i * 4 + 2], A[11]));
+}
+// Eigen::Quaterniond(Matrix3d) -> (x,y,z,w)
+__device__ void quat_from_matrix(const double* A, double* q) {
+#define M_(r, c) A[(r) * 4 + (c)]
+  const double tr = __dadd_rn(__dadd_rn(M_(0, 0), M_(1, 1)), M_(2, 2));
+  if (tr > 0.0) {
+    double t = sqrt(__dadd_rn(tr, 1.0));
+    q[3] = __dmul_rn(0.5, t); t = __ddiv_rn(0.5, t);
+    q[0] = __dmul_rn(__dsub_rn(M_(2, 1), M_(1, 2)), t);
+    q[1] = __dmul_rn(__dsub_rn(M_(0, 2), M_(2, 0)), t);
+    q[2] = __dmul_rn(__dsub_rn(M_(1, 0), M_(0, 1)), t);
+  } else {
+    int i = 0;
+    if (M_(1, 1) > M_(0, 0)) i = 1;
+    if (M_(2, 2) > M_(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = sqrt(__dadd_rn(__dsub_rn(__dsub_rn(M_(i, i), M_(j, j)), M_(k, k)), 1.0));
+    q[i] = __dmul_rn(0.5, t); t = __ddiv_rn(0.5, t);
+    q[3] = __dmul_rn(__dsub_rn(M_(k, j), M_(j, k)), t);
+    q[j] = __dmul_rn(__dadd_rn(M_(j, i), M_(i, j)), t);
+    q[k] = __dmul_rn(__dadd_rn(M_(k, i), M_(i, k)), t);
+  }
+#undef M_
+}
+
+__global__ void k_predict(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.x;
+  if (threadIdx.x != 0) return;
+  OdomState& os = d.ostate[lane_b];
+  FrameDiagDev& dg = d.diag[lane_b];
+  dg.n_map[0] = dg.n_map[1] = 0; dg.n_matches[0] = dg.n_matches[1] = 0;
+  for (int k = 0; k < 2; ++k) { SolveSummaryDev z = {}; dg.solve[k] = z; }
+  if (os.init) {
+    double inv[12], rel[12], pred[12];
+    iso_inverse(os.prev, inv);
+    iso_mul(inv, os.odom, rel);
+    iso_mul(os.odom, rel, pred);
+    for (int k = 0; k < 12; ++k) { os.prev[k] = os.odom[k]; os.odom[k] = pred[k]; }
+    quat_from_matrix(os.odom, os.q);
+    os.t[0] = os.odom[3]; os.t[1] = os.odom[7]; os.t[2] = os.odom[11];
+  }
+  for (int k = 0; k < 12; ++k) dg.pred_pose[k] = os.odom[k];
+  dg.pred_pose[12] = dg.pred_pose[13] = dg.pred_pose[14] = 0.0; dg.pred_pose[15] = 1.0;
+}
+
+int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
+  k_predict<<<lr.nlanes, 32, 0, s>>>(d, lr.lane0);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// association: one warp per edge. grid (ceil(Ecap/8), nlanes), 256 threads.
+// ---------------------------------------------------------------------------------------
+// cyclic Jacobi eigenvalues of a symmetric 3x3, +,-,*,/,sqrt only: the same operation
+// sequence as the oracle's sym3_eigenvalues (stands in for Eigen::SelfAdjointEigenSolver).
+__device__ void sym3_eigenvalues(double a00, double a01, double a02, double a11, double a12, double a22, double* w) {
+#define MUL __dmul_rn
+#define ADD __dadd_rn
+#define SUB __dsub_rn
+#define DIV __ddiv_rn
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = ADD(ADD(MUL(a01, a01), MUL(a02, a02)), MUL(a12, a12));
+    const double diag = ADD(ADD(MUL(a00, a00), MUL(a11, a11)), MUL(a22, a22));
+    if (off <= MUL(1e-32, diag) || off == 0.0) break;
+    if (a01 != 0.0) {
+      const double theta = DIV(SUB(a11, a00), MUL(2.0, a01));
+      const double t = DIV(theta >= 0 ? 1.0 : -1.0, ADD(fabs(theta), sqrt(ADD(MUL(theta, theta), 1.0))));
+      const double c = DIV(1.0, sqrt(ADD(MUL(t, t), 1.0))), s = MUL(t, c);
+      const double n00 = SUB(a00, MUL(t, a01)), n11 = ADD(a11, MUL(t, a01));
+      const double n02 = SUB(MUL(c, a02), MUL(s, a12)), n12 = ADD(MUL(s, a02), MUL(c, a12));
+      a00 = n00; a11 = n11; a01 = 0.0; a02 = n02; a12 = n12;
+    }
+    if (a02 != 0.0) {
+      const double theta = DIV(SUB(a22, a00), MUL(2.0, a02));
+      const double t = DIV(theta >= 0 ? 1.0 : -1.0, ADD(fabs(theta), sqrt(ADD(MUL(theta, theta), 1.0))));
+      const double c = DIV(1.0, sqrt(ADD(MUL(t, t), 1.0))), s = MUL(t, c);
+      const double n00 = SUB(a00, MUL(t, a02)), n22 = ADD(a22, MUL(t, a02));
+      const double n01 = SUB(MUL(c, a01), MUL(s, a12)), n12 = ADD(MUL(s, a01), MUL(c, a12));
+      a00 = n00; a22 = n22; a02 = 0.0; a01 = n01; a12 = n12;
+    }
+    if (a12 != 0.0) {
+      const double theta = DIV(SUB(a22, a11), MUL(2.0, a12));
+      const double t = DIV(theta >= 0 ? 1.0 : -1.0, ADD(fabs(theta), sqrt(ADD(MUL(theta, theta), 1.0))));
+      const double c = DIV(1.0, sqrt(ADD(MUL(t, t), 1.0))), s = MUL(t, c);
+      const double n11 = SUB(a11, MUL(t, a12)), n22 = ADD(a22, MUL(t, a12));
+      const double n01 = SUB(MUL(c, a01), MUL(s, a02)), n02 = ADD(MUL(s, a01), MUL(c, a02));
+      a11 = n11; a22 = n22; a12 = 0.0; a01 = n01; a02 = n02;
+    }
+  }
+  double e0 = a00, e1 = a11, e2 = a22, tmp;
+  if (e0 > e1) { tmp = e0; e0 = e1; e1 = tmp; }
+  if (e1 > e2) { tmp = e1; e1 = e2; e2 = tmp; }
+  if (e0 > e1) { tmp = e0; e0 = e1; e1 = tmp; }
+  w[0] = e0; w[1] = e1; w[2] = e2;
+}
+
+// A.1: float(m0*x + m1*y + m2*z + m3), double, left to right
+__device__ __forceinline__ float xform_row(const double* m, double x, double y, double z) {
+  return __double2float_rn(ADD(ADD(ADD(MUL(m[0], x), MUL(m[1], y)), MUL(m[2], z)), m[3]));
+}
+
+struct Cand { float d2; int idx; int pos; };
+__device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
+
+__global__ void __launch_bounds__(256) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y;
+  const OdomState& os = d.ostate[lane_b];
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  __shared__ int s_matches;
+  if (threadIdx.x == 0) s_matches = 0;
+  __syncthreads();
+  const bool active = force || os.init;
+  const int E = os.n_edges;
+  const int e = blockIdx.x * 8 + w;
+  if (active && e < E) {
+    const WinState& ws = d.wstate[lane_b];
+    const double* T = pose_override ? pose_override : os.odom;
+    const float4 c = d.edges[(size_t)lane_b * p.Ecap + e];
+    const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
+    const int cx = (int)floorf(qx), cy = (int)floorf(qy), cz = (int)floorf(qz);
+    const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+    const unsigned mask = (unsigned)p.Hcap - 1u;
+    const unsigned long long* tab = d.htab + (size_t)lane_b * p.Hcap;
+    // coalesced bucket probes: lanes 0..26 look up one neighbour cell each
+    unsigned bstart = 0, bcnt = 0;
+    if (ln < 27 && ws.hash_points > 0) {
+      const int dz = ln / 9 - 1, dy = (ln / 3) % 3 - 1, dx = ln % 3 - 1;
+      const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz, gen);
+      unsigned slot = hash_cell(key) & mask;
+      for (;;) {
+        const unsigned long long cur = __ldg(&tab[slot]);
+        if (cur == key) {
+          bstart = d.hstart[(size_t)lane_b * p.Hcap + slot];
+          bcnt = d.hcnt[(size_t)lane_b * p.Hcap + slot] & ((1u << kCntBits) - 1u);
+          break;
+        }
+        if ((unsigned)(cur >> 48) != gen) break;  // free slot: cell is empty
+        slot = (slot + 1) & mask;
+      }
+    }
+    // scan the buckets, all lanes striding over each bucket's contiguous points
+    const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
+    float bd[5]; int bi[5], bp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { bd[k] = 3.0e38f; bi[k] = 0x7fffffff; bp[k] = -1; }
+    unsigned nonempty = __ballot_sync(0xffffffffu, bcnt > 0);
+    while (nonempty) {
+      const int src = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const unsigned st = __shfl_sync(0xffffffffu, bstart, src);
+      const unsigned cn = __shfl_sync(0xffffffffu, bcnt, src);
+      for (unsigned j = ln; j < cn; j += 32) {
+        const float4 pt = __ldg(&sorted[st + j]);
+        // flann::L2_Simple<float>: result += diff*diff over x, y, z in float
+        const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+        const int idx = __float_as_int(pt.w);
+        if (d2 < 1.0f && cand_less(d2, idx, bd[4], bi[4])) {
+          bd[4] = d2; bi[4] = idx; bp[4] = (int)(st + j);
+#pragma unroll
+          for (int k = 4; k > 0; --k)
+            if (cand_less(bd[k], bi[k], bd[k - 1], bi[k - 1])) {
+              const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
+              const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
+              const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
+            }
+        }
+      }
+    }
+    // warp merge of the per-lane sorted lists: 5 rounds of arg-min, winner pops its head
+    float nd[5]; int ni[5], npos[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      float md = bd[0]; int mi = bi[0]; int ml = ln;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, md, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        const int ol = __shfl_xor_sync(0xffffffffu, ml, o);
+        if (cand_less(od, oi, md, mi) || (od == md && oi == mi && ol < ml)) { md = od; mi = oi; ml = ol; }
+      }
+      nd[r] = md; ni[r] = mi;
+      npos[r] = __shfl_sync(0xffffffffu, bp[0], ml);
+      if (ln == ml) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { bd[k] = bd[k + 1]; bi[k] = bi[k + 1]; bp[k] = bp[k + 1]; }
+        bd[4] = 3.0e38f; bi[4] = 0x7fffffff; bp[4] = -1;
+      }
+    }
+    if (ln == 0) {
+      uint8_t gt = 0;
+      double ev[3] = {0.0, 0.0, 0.0};
+      float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+      if (ni[4] != 0x7fffffff) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
+        gt |= 1;
+        float4 nn[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) nn[r] = sorted[npos[r]];
+        // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
+        double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) { mx = ADD(mx, (double)nn[r].x); my = ADD(my, (double)nn[r].y); mz = ADD(mz, (double)nn[r].z); }
+        mx = DIV(mx, 5.0); my = DIV(my, 5.0); mz = DIV(mz, 5.0);
+        double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const double dx = SUB((double)nn[r].x, mx), dy = SUB((double)nn[r].y, my), dz = SUB((double)nn[r].z, mz);
+          c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
+          c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
+        }
+        sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
+        if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
+      }
+      float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
+      blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;
+      blk[6] = b.x; blk[7] = b.y; blk[8] = b.z; blk[9] = (gt & 2) ? 1.0f : 0.0f;
+      if (gt & 2) atomicAdd(&s_matches, 1);
+      if (d.gate) {
+        const size_t o = (size_t)lane_b * p.Ecap + e;
+        d.gate[o] = gt;
+        for (int r = 0; r < 5; ++r) {
+          d.knn_idx[o * 5 + r] = ni[r] == 0x7fffffff ? -1 : ni[r];
+          d.knn_d2[o * 5 + r] = ni[r] == 0x7fffffff ? __int_as_float(0x7f800000) : nd[r];
+        }
+        d.eig[o * 3] = ev[0]; d.eig[o * 3 + 1] = ev[1]; d.eig[o * 3 + 2] = ev[2];
+        d.q_world[o] = make_float4(qx, qy, qz, c.w);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && active) {
+    if (s_matches) atomicAdd(&d.diag[lane_b].n_matches[outer_it], s_matches);
+    if (blockIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
+  }
+}
+#undef MUL
+#undef ADD
+#undef SUB
+#undef DIV
+
+int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
+  const dim3 g((d.p.Ecap + 7) / 8, lr.nlanes);
+  k_associate<<<g, 256, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// window update (src/laser_odometry.cc:231-235 and the first-frame branch :121-136)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_window_update(DevBuffers d, int lane0) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.x;
+  OdomState& os = d.ostate[lane_b];
+  WinState& ws = d.wstate[lane_b];
+  const int E = os.n_edges;
+  const int s = (ws.head + ws.nframes) % p.slots;
+  float4* slab = d.win + ((size_t)lane_b * p.slots + s) * p.Ecap;
+  const float4* edges = d.edges + (size_t)lane_b * p.Ecap;
+  const bool init = os.init != 0;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    const float4 c = edges[i];
+    if (!init) slab[i] = c;  // first frame: lmap_manager.addPointCloud(feats) untouched
+    else {
+      const double* T = os.odom;
+      slab[i] = make_float4(__double2float_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], c.x), __dmul_rn(T[1], c.y)), __dmul_rn(T[2], c.z)), T[3])),
+                            __double2float_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], c.x), __dmul_rn(T[5], c.y)), __dmul_rn(T[6], c.z)), T[7])),
+                            __double2float_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], c.x), __dmul_rn(T[9], c.y)), __dmul_rn(T[10], c.z)), T[11])),
+                            c.w);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    win_commit(d, lane_b, E);
+    hash_begin(d, lane_b);
+    os.init = 1; os.frame++;
+    double* po = d.poses_out + (size_t)lane_b * 16;
+    for (int k = 0; k < 12; ++k) po[k] = os.odom[k];
+    po[12] = po[13] = po[14] = 0.0; po[15] = 1.0;
+  }
+}
+
+int launch_window_update(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
+  k_window_update<<<lr.nlanes, 1024, 0, s>>>(d, lr.lane0);
+  return 1 + launch_hash_build(d, s, lr);
+}
+
+// LocalMapManager::addPointCloud from a device staging buffer (API / tests).
+__global__ void __launch_bounds__(1024) k_lmap_add(DevBuffers d, int lane_b, const float4* pts, int n) {
+  const DevParams& p = d.p;
+  WinState& ws = d.wstate[lane_b];
+  const int s = (ws.head + ws.nframes) % p.slots;
+  float4* slab = d.win + ((size_t)lane_b * p.slots + s) * p.Ecap;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) slab[i] = pts[i];
+  __syncthreads();
+  if (threadIdx.x == 0) { win_commit(d, lane_b, n); hash_begin(d, lane_b); }
+}
+
+int launch_lmap_add(const DevBuffers& d, cudaStream_t s, int lane, const float4* pts_dev, int n) {
+  k_lmap_add<<<1, 1024, 0, s>>>(d, lane, pts_dev, n);
+  return 1 + launch_hash_build(d, s, LaneRange{lane, 1});
+}
+
+// rebuild the hash of one lane after the window / received map was edited from the host
+__global__ void k_hash_begin(DevBuffers d, int lane_b) { if (threadIdx.x == 0) hash_begin(d, lane_b); }
+int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane) {
+  k_hash_begin<<<1, 32, 0, s>>>(d, lane);
+  return 1 + launch_hash_build(d, s, LaneRange{lane, 1});
+}
+
+// gather the window in logical order (LocalMapManager::getLocalMap)
+__global__ void __launch_bounds__(256) k_lmap_gather(DevBuffers d, int lane_b, float4* out) {
+  __shared__ WinView v;
+  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.total; i += gridDim.x * blockDim.x) out[i] = win_point(d, lane_b, v, i);
+}
+int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out) {
+  k_lmap_gather<<<64, 256, 0, s>>>(d, lane, out);
+  return 1;
+}
+
+}  // namespace liodom
