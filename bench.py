@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — LiODOM hot path (extract + register) on B200: scans/s, roofline, CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # restated CPU path (oracle port)
+
+A step = one pass of the hot path (ring split -> curvature/edge selection -> predict ->
+2 x {voxel-hash 5-NN association + line gate, on-device LM} -> window update + hash rebuild)
+over one batch of `lanes` independent HDL-64-shaped synthetic scans (config C1 of
+BASELINE.json, launch/liodom.launch params).  `value` is scans/s with the scans resident in
+HBM; `e2e` is the same metric through the C-ABI call with pinned HOST buffers, H2D copy of the
+scans and D2H read of the poses inside the timed region.  Under torchrun every rank runs its
+own lanes (no data-path collective; weak scaling) and rank 0 prints one JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hdl64_scans_per_sec_extract_plus_register"
+UNIT = "scans/s"
+N_SEEDS = 8          # distinct synthetic sequences (seeds 1000..1007)
+BYTES_PER_POINT = 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LIODOM_BENCH_LANES", "32")),
+                    help="independent sequences per GPU processed by one step")
+    ap.add_argument("--sensor", default="hdl64")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-pass", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_sequences(sensor, rank, nseq, nframes):
+    """nseq sequences x nframes scans (float32 [n,4]); seeds are distinct across ranks."""
+    from liodom_b200 import synth
+    out = []
+    for s in range(nseq):
+        seed = 1000 + rank * N_SEEDS + s
+        scans, _ = synth.sequence(sensor, seed, nframes)
+        out.append(scans)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from liodom_b200 import api
+
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, K, W = args.lanes, args.steps, args.warmup
+    nframes = W + K
+    nseq = min(B, N_SEEDS)
+    t0 = time.time()
+    seqs = make_sequences(args.sensor, rank, nseq, nframes)
+    gen_s = time.time() - t0
+    npts = np.array([[len(seqs[s][f]) for f in range(nframes)] for s in range(nseq)])
+    max_points = 131072 if args.sensor == "hdl64" else 1 << 20
+    kw = dict(prev_frames=15, max_points=max_points)   # launch/liodom.launch:17-31
+
+    # inputs resident in HBM: one tensor per (sequence, frame)
+    dev_scans = [[torch.from_numpy(seqs[s][f]).to(dev) for f in range(nframes)] for s in range(nseq)]
+    # pinned host copies for the end-to-end leg
+    host_scans = [[torch.from_numpy(seqs[s][f]).pin_memory() for f in range(nframes)] for s in range(nseq)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident leg (value) -------------------------------------------
+    ctx = api.Context(batch=B, device=local, **kw)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_dev(f):
+        ptrs = [dev_scans[l % nseq][f].data_ptr() for l in range(B)]
+        cnts = [int(npts[l % nseq][f]) for l in range(B)]
+        ctx.scan_batch_ptrs(ptrs, cnts, BYTES_PER_POINT, on_device=True)
+
+    for f in range(W):
+        step_dev(f)
+    ctx.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for f in range(W, W + K):
+        step_dev(f)
+    ev1.record(stream)
+    ctx.sync()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    poses_dev, nedges = ctx.results()
+    diags = [ctx.scan_diag(l) for l in range(min(B, nseq))]
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---------------- per-stage pass (roofline of the dominant kernel) ----------------------
+    roof = None
+    stages = None
+    if not args.no_stage_pass:
+        for l in range(B):
+            ctx.reset(l)
+        E_sum = M_sum = Ev_sum = pass_sum = 0.0
+        nd = 0
+        for f in range(W + K):
+            if f == W:
+                ctx.stage_timing(True)
+            step_dev(f)
+            if f >= W:
+                ctx.sync()
+                for l in range(min(B, nseq)):
+                    d = ctx.scan_diag(l)
+                    E_sum += d.n_edges
+                    M_sum += 0.5 * (d.n_map[0] + d.n_map[1])
+                    Ev_sum += 0.5 * (d.n_matches[0] + d.n_matches[1])
+                    pass_sum += 0.5 * sum(d.solve[i].jac_evals + d.solve[i].cost_evals for i in range(2))
+                    nd += 1
+        ms, calls = ctx.stage_times()
+        ctx.stage_timing(False)
+        per_call = ms / max(calls, 1)
+        E, M, Ev, passes = E_sum / nd, M_sum / nd, Ev_sum / nd, pass_sum / nd
+        Npts = float(npts[:, W:].mean())
+        # algorithmic bytes per launch, all lanes of one step
+        alg = {
+            "split": B * (BYTES_PER_POINT * Npts * 2),                     # read scan, write ring-major copy
+            "extract": B * (BYTES_PER_POINT * Npts + BYTES_PER_POINT * E),
+            "associate": B * (16 * E + 16 * M + 56 * E),
+            "solve": B * (passes * 40 * E + 224),
+            "window+hash": B * (16 * E + 2 * 16 * M),
+        }
+        groups = {"split": per_call[0], "extract": per_call[1], "associate": 0.5 * (per_call[2] + per_call[4]),
+                  "solve": 0.5 * (per_call[3] + per_call[5]), "window+hash": per_call[6]}
+        share = {"split": per_call[0], "extract": per_call[1], "associate": per_call[2] + per_call[4],
+                 "solve": per_call[3] + per_call[5], "window+hash": per_call[6]}
+        tot = sum(share.values())
+        dom = max(share, key=share.get)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg[dom] / (groups[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": int(alg[dom]), "launch_ms": round(groups[dom], 4)}
+        stages = {"ms_per_step": {k: round(v, 4) for k, v in share.items()},
+                  "share": {k: round(v / tot, 4) for k, v in share.items()},
+                  "gbps": {k: round(alg[k] / (groups[k] * 1e-3) / 1e9, 2) for k in alg},
+                  "per_scan": {"points": round(Npts, 1), "edges": round(E, 1), "map_points": round(M, 1),
+                               "matches": round(Ev, 1), "lm_passes_per_solve": round(passes, 2)}}
+    ctx.close()
+
+    # ---------------- end-to-end leg (host buffers through the C ABI) -----------------------
+    ctx = api.Context(batch=B, device=local, **kw)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_e2e(f):
+        ptrs = [host_scans[l % nseq][f].data_ptr() for l in range(B)]
+        cnts = [int(npts[l % nseq][f]) for l in range(B)]
+        ctx.scan_batch_ptrs(ptrs, cnts, BYTES_PER_POINT, on_device=False)
+        return ctx.results()
+
+    for f in range(W):
+        step_e2e(f)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t_wall = time.perf_counter()
+    h2d = d2h = 0
+    for f in range(W, W + K):
+        poses_e2e, ne = step_e2e(f)
+        h2d += sum(int(npts[l % nseq][f]) for l in range(B)) * BYTES_PER_POINT
+        d2h += poses_e2e.nbytes + ne.nbytes
+    ev1.record(stream)
+    ctx.sync()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    # the two legs must agree on the answer: same scans, same start state
+    same = bool(np.array_equal(poses_e2e, poses_dev))
+    ctx.close()
+
+    # ---------------- CPU baseline (restated reference path, rank 0, N=1 only) --------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single_stream(seqs, budget_s=15.0)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 selection/kNN, f64 gates+LM", "data": "synthetic",
+        "config": {"workload": "C1: HDL-64-shaped ray-cast urban sequences (~118k pts/scan), launch/liodom.launch params "
+                               "(scan_regions=8, edges_per_region=10, prev_frames=15, range 3-75 m), extract+register",
+                   "lanes_per_gpu": B, "distinct_sequences_per_gpu": nseq, "points_per_scan": int(npts.mean()),
+                   "sharding": "independent sequences per GPU, no collective",
+                   "l2": "every step reads a distinct scan batch (%d MB/step/GPU; %d MB over the run > 126 MB L2), uploaded before timing"
+                         % (int(B * npts.mean() * 16 / 1e6), int(nseq * npts.sum(axis=1).mean() * 16 / 1e6))},
+        "ms_per_scan": round(ms_total / K / B, 5),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
+                "ms_per_step": round(e2e_ms / K, 4), "same_poses_as_device_leg": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "synth_seconds": round(gen_s, 1),
+    }
+    if roof is not None:
+        out["roofline"] = roof
+        out["stages"] = stages
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+
+
+def cpu_baseline_single_stream(seqs, budget_s):
+    """The oracle port with the reference's own threading (OpenMP curvature loop with
+    max(2, nthreads-5) threads, solver threads = nproc), one stream after another."""
+    import oracle
+    op = oracle.make_params(prev_frames=15)
+    n = 0
+    t0 = time.perf_counter()
+    stage = np.zeros(5)
+    for scans in seqs:
+        _, st, _ = oracle.run_sequence(op, scans)
+        stage += st
+        n += len(scans)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d scans of the same C1 sequences, single stream, reference threading (restated CPU path; "
+                      "the reference binary needs ROS/PCL/Ceres and cannot be built here)" % n,
+            "ms_per_scan": round(dt / n * 1e3, 3),
+            "stage_ms_per_scan": {k: round(v / n / 1e3, 3) for k, v in zip(("split", "extract", "associate", "solve", "window"), stage)}}
+
+
+def run_reference(args):
+    """Reference arm: the restated CPU path on the host cores, one independent sequence per
+    worker thread (the same sharding the GPU arm uses), all cores busy."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    K, W = args.steps, args.warmup
+    cores = os.cpu_count() or 1
+    workers = cores
+    nframes = W + K
+    nseq = min(workers, N_SEEDS)
+    seqs = make_sequences(args.sensor, 0, nseq, nframes)
+    op = oracle.make_params(prev_frames=15, omp_threads=1)
+    odos = [oracle.Odometer(op) for _ in range(workers)]
+
+    def one(wf):
+        w, f = wf
+        s = seqs[w % nseq][f]
+        edges, _ = oracle.extract_scan(op, s)
+        odos[w].process(edges)
+        return len(edges)
+
+    pool = ThreadPoolExecutor(workers)
+    for f in range(W):
+        list(pool.map(one, [(w, f) for w in range(workers)]))
+    t0 = time.perf_counter()
+    for f in range(W, W + K):
+        list(pool.map(one, [(w, f) for w in range(workers)]))
+    dt = time.perf_counter() - t0
+    pool.shutdown()
+    value = workers * K / dt
+    npts = int(np.mean([len(s) for s in seqs[0]]))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 selection/kNN, f64 gates+LM", "data": "synthetic",
+        "config": {"workload": "C1: HDL-64-shaped ray-cast urban sequences (~118k pts/scan), launch/liodom.launch params, "
+                               "extract+register", "lanes": workers, "points_per_scan": npts},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d workers x %d scans, one independent sequence per host thread (restated CPU path: "
+                                   "the reference binary needs ROS/PCL/Ceres and cannot be built here)" % (workers, K)},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

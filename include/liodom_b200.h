@@ -141,10 +141,21 @@ int liodom_scan_batch(liodom_ctx* ctx, const void* const* pts, const int* n, int
                       int width, int height, int on_device);
 /* poses16_out[batch*16], n_edges_out[batch] (either may be NULL) of the last enqueued scan. */
 int liodom_scan_results(liodom_ctx* ctx, double* poses16_out, int* n_edges_out);
+/* Diagnostics of the last scan of a lane (map sizes, matches, solver summaries); synchronises. */
+int liodom_scan_diag(liodom_ctx* ctx, int lane, liodom_frame_diag* diag);
 /* Edges of the last scan of a lane (device -> host). */
 int liodom_scan_edges(liodom_ctx* ctx, int lane, float* edges_xyzi, int cap, int* n_edges);
 /* Number of kernel launches enqueued by this context so far (bench gpu_launches). */
 long long liodom_launch_count(const liodom_ctx* ctx);
+
+/* Per-stage device timing of liodom_scan_batch (CUDA events on the context's stream); the
+ * counterpart of the reference's Stats timers (src/stats.cc:41-71), with the ring split
+ * reported separately (the reference's extraction span excludes it, src/feature_extractor.cc:53-55).
+ * Stages: 0 split, 1 extract, 2 predict+associate(outer 0), 3 solve(0), 4 associate(1),
+ * 5 solve(1), 6 window update + voxel-hash rebuild. */
+#define LIODOM_NUM_STAGES 7
+int liodom_stage_timing(liodom_ctx* ctx, int enable);  /* (re)starts accumulation; synchronises */
+int liodom_stage_times(liodom_ctx* ctx, double* ms_out /*[LIODOM_NUM_STAGES]*/, int* n_calls);
 
 /* ---- Map (src/map.cc:70-189, include/liodom/map.h:94-116) --------------------------- */
 typedef struct liodom_map liodom_map;

@@ -32,6 +32,10 @@ class FrameDiag(ctypes.Structure):
                 ("solve", SolveSummary * 2), ("pred_pose", ctypes.c_double * 16)]
 
 
+NUM_STAGES = 7
+STAGE_NAMES = ("split", "extract", "associate0", "solve0", "associate1", "solve1", "window+hash")
+
+
 class LiodomError(RuntimeError):
     pass
 
@@ -51,6 +55,8 @@ def load():
         L.liodom_last_error.argtypes = [_vp]
         L.liodom_stream.restype = _vp
         L.liodom_launch_count.restype = ctypes.c_longlong
+        L.liodom_launch_count.argtypes = [_vp]
+        L.liodom_stream.argtypes = [_vp]
         if hasattr(L, "liodom_map_create"):
             L.liodom_map_last_error.restype = ctypes.c_char_p
             L.liodom_map_last_error.argtypes = [_vp]
@@ -234,6 +240,11 @@ class Context:
         self._keep = None
         return poses.reshape(-1, 4, 4), ne
 
+    def scan_diag(self, lane=0):
+        d = FrameDiag()
+        self._ck(self.lib.liodom_scan_diag(self.h, lane, ctypes.byref(d)))
+        return d
+
     def scan_edges(self, lane=0):
         out = np.empty((self.max_edges, 4), np.float32)
         n = ctypes.c_int()
@@ -242,6 +253,21 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.liodom_sync(self.h))
+
+    @property
+    def stream(self):
+        """cudaStream_t (integer address) the context enqueues on."""
+        return self.lib.liodom_stream(self.h)
+
+    def stage_timing(self, enable=True):
+        self._ck(self.lib.liodom_stage_timing(self.h, 1 if enable else 0))
+
+    def stage_times(self):
+        """-> (ms per stage summed over the timed scan_batch calls [NUM_STAGES], number of calls)."""
+        ms = np.zeros(NUM_STAGES)
+        n = ctypes.c_int()
+        self._ck(self.lib.liodom_stage_times(self.h, _p(ms), ctypes.byref(n)))
+        return ms, n.value
 
     @property
     def launch_count(self):

@@ -46,7 +46,19 @@ struct liodom_ctx {
   double* stage_pose = nullptr; // [12]
   void* h_scratch = nullptr;    // pinned
   size_t h_scratch_bytes = 0;
+  // optional per-stage device timing of liodom_scan_batch (bench roofline evidence)
+  bool stage_timing = false;
+  std::vector<cudaEvent_t> stage_events;  // LIODOM_NUM_STAGES + 1 events per timed call
 };
+
+// Record a stage boundary on the compute stream when stage timing is on.
+static void stage_mark(liodom_ctx* c) {
+  if (!c->stage_timing) return;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, c->stream);
+  c->stage_events.push_back(e);
+}
 
 static thread_local std::string g_create_err;
 
@@ -260,6 +272,7 @@ void liodom_ctx_destroy(liodom_ctx* c) {
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -502,9 +515,12 @@ static int enqueue_register(liodom_ctx* c, const DevBuffers& d, LaneRange lr) {
   k += launch_predict(d, c->stream, lr);
   for (int it = 0; it < 2; ++it) {  // src/laser_odometry.cc:198
     k += launch_associate(d, c->stream, lr, it, false, nullptr);
+    stage_mark(c);
     k += launch_solve(d, c->stream, lr, it);
+    stage_mark(c);
   }
   k += launch_window_update(d, c->stream, lr);
+  stage_mark(c);
   return k;
 }
 
@@ -513,7 +529,10 @@ int liodom_register(liodom_ctx* c, int lane, const float* edges_xyzi, int n_edge
   rc = hash_generation_guard(c, 1); if (rc) return rc;
   rc = put_edges(c, lane, edges_xyzi, n_edges); if (rc) return rc;
   const DevBuffers& d = c->dprod;
+  const bool st = c->stage_timing;  // stage timing covers liodom_scan_batch only
+  c->stage_timing = false;
   c->launches += enqueue_register(c, d, LaneRange{lane, 1});
+  c->stage_timing = st;
   CK(cudaGetLastError());
   double pose[16]; FrameDiagDev dg;
   CK(cudaMemcpyAsync(pose, d.poses_out + (size_t)lane * 16, sizeof(pose), cudaMemcpyDeviceToHost, c->stream));
@@ -560,8 +579,11 @@ int liodom_scan_batch(liodom_ctx* c, const void* const* pts, const int* n, int s
   CK(cudaMemcpyAsync(d.scan, hd, sizeof(ScanDesc) * B, cudaMemcpyHostToDevice, c->stream));
   const LaneRange lr{0, B};
   int k = 0;
+  stage_mark(c);
   k += launch_split(d, c->stream, lr);
+  stage_mark(c);
   k += launch_extract(d, c->stream, lr, false);
+  stage_mark(c);
   k += enqueue_register(c, d, lr);
   c->launches += k;
   CK(cudaGetLastError());
@@ -573,6 +595,33 @@ int liodom_scan_batch(liodom_ctx* c, const void* const* pts, const int* n, int s
   return 0;
 }
 
+int liodom_stage_timing(liodom_ctx* c, int enable) {
+  if (!c) return LIODOM_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
+  c->stage_events.clear();
+  c->stage_timing = enable != 0;
+  return 0;
+}
+
+int liodom_stage_times(liodom_ctx* c, double* ms_out, int* n_calls) {
+  if (!c || !ms_out) return LIODOM_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const size_t per = LIODOM_NUM_STAGES + 1;
+  const size_t calls = c->stage_events.size() / per;
+  for (int s = 0; s < LIODOM_NUM_STAGES; ++s) ms_out[s] = 0.0;
+  for (size_t k = 0; k < calls; ++k)
+    for (int s = 0; s < LIODOM_NUM_STAGES; ++s) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, c->stage_events[k * per + s], c->stage_events[k * per + s + 1]));
+      ms_out[s] += ms;
+    }
+  if (n_calls) *n_calls = (int)calls;
+  return 0;
+}
+
 int liodom_scan_results(liodom_ctx* c, double* poses16_out, int* n_edges_out) {
   if (!c) return LIODOM_E_INVALID;
   CK(cudaSetDevice(c->device));
@@ -580,6 +629,18 @@ int liodom_scan_results(liodom_ctx* c, double* poses16_out, int* n_edges_out) {
   if (c->in_flight[buf]) { CK(cudaEventSynchronize(c->ev_done[buf])); c->in_flight[buf] = false; }
   if (poses16_out) std::memcpy(poses16_out, c->h_poses[buf], sizeof(double) * 16 * c->batch);
   if (n_edges_out) std::memcpy(n_edges_out, c->h_nedges[buf], sizeof(int) * c->batch);
+  return 0;
+}
+
+int liodom_scan_diag(liodom_ctx* c, int lane, liodom_frame_diag* diag) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  if (!diag) return fail(c, LIODOM_E_INVALID, "diag is NULL");
+  FrameDiagDev dg;
+  CK(cudaMemcpyAsync(&dg, c->d.diag + lane, sizeof(dg), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  diag->n_edges = dg.n_edges;
+  for (int k = 0; k < 2; ++k) { diag->n_map[k] = dg.n_map[k]; diag->n_matches[k] = dg.n_matches[k]; copy_summary(dg.solve[k], &diag->solve[k]); }
+  std::memcpy(diag->pred_pose, dg.pred_pose, sizeof(dg.pred_pose));
   return 0;
 }
 

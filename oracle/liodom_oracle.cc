@@ -1072,7 +1072,10 @@ void orc_odom_process(OrcOdom* o, const float* edges_xyzi, int E, double* pose_o
       D.n_map[optim_it] = (int)local_map.size(); D.n_matches[optim_it] = blocks.matches;
       D.times_us[1] += us_since(t0);
       t0 = Clock::now();
-      Problem pb{blocks.cab.data(), blocks.matches, o->p.min_range, o->p.max_range, (int)sysconf(_SC_NPROCESSORS_ONLN)};
+      // options.num_threads = sysconf(_SC_NPROCESSORS_ONLN) (src/laser_odometry.cc:216); omp_threads > 0
+      // overrides it so that several independent sequences can share the host (bench reference arm).
+      const int solver_threads = o->p.omp_threads > 0 ? o->p.omp_threads : (int)sysconf(_SC_NPROCESSORS_ONLN);
+      Problem pb{blocks.cab.data(), blocks.matches, o->p.min_range, o->p.max_range, solver_threads};
       lm_solve(pb, o->param_q, o->param_t, 0, &D.solve[optim_it]);
       o->odom = iso_identity();  // :222-227
       matrix_from_quat(o->param_q, o->odom);

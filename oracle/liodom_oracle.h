@@ -39,7 +39,8 @@ typedef struct {
   int prev_frames;         /* 5 (launch: 15) -> local_map_size_ */
   int filter_local_map;    /* false */
   int mapping;             /* false */
-  int omp_threads;         /* 0: reference rule max(2, omp_get_max_threads()-5) */
+  int omp_threads;         /* 0: reference rules (extractor max(2, omp_get_max_threads()-5), solver nproc);
+                              >0: that many threads for both (several sequences sharing one host) */
 } OrcParams;
 
 void orc_default_params(OrcParams* p);
