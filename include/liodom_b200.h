@@ -68,7 +68,7 @@ int liodom_sync(liodom_ctx* ctx);
  * tests.  Host buffers; any output may be NULL.
  *  ring_of_point[n]  ring id or -1;  rings_xyzi[4*n] ring-major stable compaction;
  *  ring_offsets[scan_lines+1];  src_index[n] input index of each compacted point.
- *  n_ambiguous: points whose ring bin is within 1e-9 of a boundary (GPU atan vs libm). */
+ *  n_ambiguous: points whose ring bin is within 1e-12 of a boundary (GPU atan vs libm). */
 int liodom_split(liodom_ctx* ctx, int lane, const void* pts, int n, int stride_bytes,
                  int width, int height, int32_t* ring_of_point, float* rings_xyzi,
                  int32_t* ring_offsets, int32_t* src_index, int* n_valid, int* n_ambiguous);

@@ -128,7 +128,7 @@ class Context:
         src = np.empty(n, np.int32)
         nv = ctypes.c_int()
         na = ctypes.c_int()
-        self._ck(self.lib.liodom_split(self.h, lane, _p(pts), n, pts.strides[0], width, height, _p(ring), _p(rings),
+        self._ck(self.lib.liodom_split(self.h, lane, _p(pts), n, pts.shape[1] * 4, width, height, _p(ring), _p(rings),
                                        _p(off), _p(src), ctypes.byref(nv), ctypes.byref(na)))
         return dict(ring_of_point=ring, rings=rings[:nv.value].copy(), offsets=off, src_index=src[:nv.value].copy(),
                     n_valid=nv.value, n_ambiguous=na.value)
@@ -143,7 +143,7 @@ class Context:
             er = np.empty(self.max_edges, np.int32)
             ei = np.empty(self.max_edges, np.int32)
             keys = np.full(max(n, 1), np.nan, np.float64)
-        self._ck(self.lib.liodom_extract(self.h, lane, _p(pts), n, pts.strides[0], width, height, _p(edges),
+        self._ck(self.lib.liodom_extract(self.h, lane, _p(pts), n, pts.shape[1] * 4, width, height, _p(edges),
                                          ctypes.byref(ne), _p(er), _p(ei), _p(keys)))
         e = ne.value
         if not debug:
@@ -221,7 +221,7 @@ class Context:
         """scans: list of `batch` float32 host arrays [n,4] (or [n,8] PCL layout)."""
         assert len(scans) == self.batch
         arrs = [_pts(s) for s in scans]
-        stride = arrs[0].strides[0]
+        stride = arrs[0].shape[1] * 4
         ptrs = (_vp * self.batch)(*[a.ctypes.data for a in arrs])
         ns = (ctypes.c_int * self.batch)(*[len(a) for a in arrs])
         self._keep = arrs  # keep alive until results()

@@ -38,10 +38,13 @@ __device__ __forceinline__ float4 load_xyzi(const ScanDesc& sc, int i) {
   return v;
 }
 
-__device__ __forceinline__ bool near_int(double v) { return fabs(v - rint(v)) < 1e-9; }
+// Device atan is <= 2 ulp, glibc <= 1 ulp; after *180/pi and the affine bin map the two can differ by
+// < 1e-13 in `v`. Decisions closer than kAmbTol to a boundary are counted as ambiguous.
+constexpr double kAmbTol = 1e-12;
+__device__ __forceinline__ bool near_int(double v) { return fabs(v - rint(v)) < kAmbTol; }
 
-// Returns ring id or -1. `amb` is set when a bin decision sits within 1e-9 of a boundary
-// (device atan is <=2 ulp, libm <=1 ulp: such a point could land in the other bin).
+// Returns ring id or -1. `amb` is set when a bin decision sits within kAmbTol of a boundary
+// (such a point could land in the other bin under a different libm).
 __device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, bool& amb) {
   const double x = xf, y = yf, z = zf;
   bool valid = isfinite(x) && isfinite(y) && isfinite(z);
@@ -59,7 +62,12 @@ __device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, floa
     double v;
     if (angle >= -8.83) { v = __dadd_rn(__dmul_rn(__dsub_rn(2.0, angle), 3.0), 0.5); id = __double2int_rz(v); }
     else { v = __dadd_rn(__dmul_rn(__dsub_rn(-8.83, angle), 2.0), 0.5); id = 32 + __double2int_rz(v); }
-    amb = near_int(v) || fabs(angle + 8.83) < 1e-9 || fabs(angle - 2.0) < 1e-9 || fabs(angle + 24.33) < 1e-9;
+    amb = near_int(v) || fabs(angle - 2.0) < kAmbTol || fabs(angle + 24.33) < kAmbTol;
+    if (fabs(angle + 8.83) < kAmbTol) {  // branch boundary: ambiguous only if the two formulas disagree
+      const int hi = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn(2.0, angle), 3.0), 0.5));
+      const int lo = 32 + __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn(-8.83, angle), 2.0), 0.5));
+      amb = amb || hi != lo;
+    }
     if (angle > 2.0 || angle < -24.33 || id > 63 || id < 0) id = -1;
   } else if (p.scan_lines == 32) {
     const double v = __ddiv_rn(__dmul_rn(__dadd_rn(angle, 92.0 / 3.0), 3.0), 4.0);

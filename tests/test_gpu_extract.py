@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _cmp_split(g, o):
-    assert g["n_ambiguous"] == 0, "scan has ring-bin decisions within 1e-9 of a boundary"
+    assert g["n_ambiguous"] == 0, "scan has ring-bin decisions within 1e-12 of a boundary"
     assert np.array_equal(g["ring_of_point"], o["ring_of_point"])
     assert np.array_equal(g["offsets"], o["offsets"])
     assert np.array_equal(g["src_index"], o["src_index"])
