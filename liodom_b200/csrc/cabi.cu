@@ -211,11 +211,13 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.wstate, B));
   CKC(dalloc(c, &d.ostate, B));
   CKC(dalloc(c, &d.sorted, B * p.Mcap));
+  CKC(dalloc(c, &d.lin, B * p.Mcap));
   CKC(dalloc(c, &d.htab, B * p.Hcap));
   CKC(dalloc(c, &d.hcnt, B * p.Hcap));
   CKC(dalloc(c, &d.hstart, B * p.Hcap));
   CKC(dalloc(c, &d.pt_slot, B * p.Mcap));
   CKC(dalloc(c, &d.pt_rank, B * p.Mcap));
+  CKC(dalloc(c, &d.perm, B * p.Ecap));
   CKC(dalloc(c, &d.blocks, B * p.Ecap * 10));
   CKC(dalloc(c, &d.knn_idx, B * p.Ecap * 5));
   CKC(dalloc(c, &d.knn_d2, B * p.Ecap * 5));

@@ -9,8 +9,10 @@
 //   slots        B x Ecap float4        edges in fixed (ring, region, pick) slots
 //   edges        B x Ecap float4        compacted edges (sensor frame)
 //   win          B x S x Ecap float4    sliding window slabs (world frame), S = prev_frames+1
-//   sorted       B x Mcap float4        window points bucketed by 1 m voxel (w = logical index)
+//   sorted       B x Mcap float4        window points bucketed by 0.5 m voxel (w = logical index)
+//   lin          B x Mcap float4        window (+ received map) in logical order, for neighbour fetches
 //   htab/hcnt/hstart  B x Hcap          open-addressing voxel hash (generation tagged)
+//   perm         B x Ecap i32           edges in Morton order of their predicted world cell
 //   blocks       B x Ecap x 10 f32      residual blocks {c, a, b, valid}
 #pragma once
 #include <cuda_runtime.h>
@@ -109,11 +111,13 @@ struct DevBuffers {
   WinState* wstate;        // [B]
   OdomState* ostate;       // [B]
   float4* sorted;          // [B][Mcap]
+  float4* lin;             // [B][Mcap] the same points in logical (window) order
   unsigned long long* htab;  // [B][Hcap]
   unsigned* hcnt;          // [B][Hcap]
   unsigned* hstart;        // [B][Hcap]
   unsigned* pt_slot;       // [B][Mcap]
   unsigned* pt_rank;       // [B][Mcap]
+  int* perm;               // [B][Ecap] Morton-ordered edge indices (thread -> edge) of k_associate
   float* blocks;           // [B][Ecap][10]
   int* knn_idx;            // [B][Ecap][5] (debug) or null
   float* knn_d2;           // [B][Ecap][5]
@@ -131,7 +135,7 @@ int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys);
 int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane);
-int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr);  // + Morton ordering of the edges
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override);
 int launch_solve(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it);
 int launch_solve_blocks(const DevBuffers& d, cudaStream_t s, int lane, const double* cab, int n, double* qt_inout,
@@ -146,9 +150,12 @@ __device__ __forceinline__ unsigned long long pack_cell(int ix, int iy, int iz, 
   return ((unsigned long long)gen << 48) | ((unsigned long long)(iz & 0xFFFF) << 32) |
          ((unsigned long long)(iy & 0xFFFF) << 16) | (unsigned long long)(ix & 0xFFFF);
 }
+// kNN voxel: 0.5 m (x * 2 is exact in float, so the cell of a point is well defined).
+__device__ __forceinline__ int cell_of(float v) { return (int)floorf(v * 2.0f); }
 __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+  // murmur3 fmix64 of the 48-bit cell key: every key bit reaches the low (slot) bits
   k &= 0xFFFFFFFFFFFFull;
-  k ^= k >> 23; k *= 0x2127599BF4325C37ull; k ^= k >> 47;
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (unsigned)k;
 }
 

@@ -1,4 +1,4 @@
-// LaserOdometer data association on sm_100a: sliding window (LocalMapManager), 1 m
+// LaserOdometer data association on sm_100a: sliding window (LocalMapManager), 0.5 m
 // open-addressing voxel hash, exact 5-NN, line gate and residual-block assembly
 // (replaces src/laser_odometry.cc:24-69, :148-150, :186-195, :231-235, :300-361).
 //
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
     const float4 pt = win_point(d, lane_b, v, i);
     unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
     if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { *pslot = 0xffffffffu; continue; }  // PCL kd-tree skips these
-    const unsigned long long mine = pack_cell((int)floorf(pt.x), (int)floorf(pt.y), (int)floorf(pt.z), gen);
+    const unsigned long long mine = pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen);
     unsigned slot = hash_cell(mine) & mask;
     bool owner = false;
     for (;;) {
@@ -120,8 +120,9 @@ __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
   float4* sorted = d.sorted + (size_t)lane_b * d.p.Mcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
-    if (ps == 0xffffffffu) continue;
     float4 pt = win_point(d, lane_b, v, i);
+    d.lin[(size_t)lane_b * d.p.Mcap + i] = pt;
+    if (ps == 0xffffffffu) continue;
     pt.w = __int_as_float(i);
     sorted[start[ps & 0x7fffffffu] + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
   }
@@ -197,9 +198,69 @@ __global__ void k_predict(DevBuffers d, int lane0) {
   dg.pred_pose[12] = dg.pred_pose[13] = dg.pred_pose[14] = 0.0; dg.pred_pose[15] = 1.0;
 }
 
+// Morton ordering of the edges by the 0.5 m cell of their predicted world position: threads of
+// one k_associate warp then walk the same / neighbouring hash buckets (broadcast loads, similar
+// trip counts).  Only the thread -> edge assignment changes; outputs stay in edge order.
+// One CTA sorts a chunk of kOrderChunk edges in shared memory (bitonic, 64-bit key|index).
+constexpr int kOrderChunk = 8192;
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y;
+  const OdomState& os = d.ostate[lane_b];
+  const int base = blockIdx.x * kOrderChunk;
+  const int n = min(kOrderChunk, os.n_edges - base);
+  if (n <= 0) return;
+  extern __shared__ unsigned long long sk[];
+  int np2 = 32;
+  while (np2 < n) np2 <<= 1;
+  const float4* edges = d.edges + (size_t)lane_b * p.Ecap + base;
+  const float m0 = (float)os.odom[0], m1 = (float)os.odom[1], m2 = (float)os.odom[2], m3 = (float)os.odom[3];
+  const float m4 = (float)os.odom[4], m5 = (float)os.odom[5], m6 = (float)os.odom[6], m7 = (float)os.odom[7];
+  const float m8 = (float)os.odom[8], m9 = (float)os.odom[9], m10 = (float)os.odom[10], m11 = (float)os.odom[11];
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    unsigned long long v = ~0ull;
+    if (i < n) {
+      const float4 c = edges[i];
+      const float x = m0 * c.x + m1 * c.y + m2 * c.z + m3, y = m4 * c.x + m5 * c.y + m6 * c.z + m7, z = m8 * c.x + m9 * c.y + m10 * c.z + m11;
+      unsigned key = 0x3fffffffu;  // non-finite edges last
+      if (isfinite(x) && isfinite(y) && isfinite(z))
+        key = spread10((unsigned)cell_of(x)) | (spread10((unsigned)cell_of(y)) << 1) | (spread10((unsigned)cell_of(z)) << 2);
+      v = ((unsigned long long)key << 32) | (unsigned)i;
+    }
+    sk[i] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+        const unsigned long long a = sk[lo], b = sk[hi];
+        const bool up = (lo & k) == 0;
+        if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  int* perm = d.perm + (size_t)lane_b * p.Ecap + base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = base + (int)(unsigned)(sk[i] & 0xffffffffull);
+}
+
 int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   k_predict<<<lr.nlanes, 32, 0, s>>>(d, lr.lane0);
-  return 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_edge_order, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrderChunk * 8);
+    configured = true;
+  }
+  k_edge_order<<<dim3((d.p.Ecap + kOrderChunk - 1) / kOrderChunk, lr.nlanes), 1024, kOrderChunk * 8, s>>>(d, lr.lane0);
+  return 2;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -253,140 +314,193 @@ __device__ __forceinline__ float xform_row(const double* m, double x, double y, 
   return __double2float_rn(ADD(ADD(ADD(MUL(m[0], x), MUL(m[1], y)), MUL(m[2], z)), m[3]));
 }
 
-struct Cand { float d2; int idx; int pos; };
 __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) { return d2a < d2b || (d2a == d2b && ia < ib); }
 
-__global__ void __launch_bounds__(256) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override) {
+// Exact 5-NN of one query, one thread per edge, over the kCell = 0.5 m voxel hash.
+//
+// Exactness.  Every map point with float d2 < (0.5 R)^2 lies inside the (2R+1)^3 cell cube
+// around the query's cell: an outside point differs by >= 0.5 R on some axis, and float
+// subtraction, squaring and summation are monotone.  So after the 27-cell cube the list is
+// final iff its 5th entry has d2 < 0.25; otherwise the 98 cells of the next shell are added,
+// which is exact for the reference's gate d2[4] < 1.0 (src/laser_odometry.cc:324).
+// Pruning.  cell_min_d2 evaluates L2_Simple on the per-axis gaps to the cell box with the same
+// float operations as the point distance, hence it is <= the float d2 of every point of the
+// cell; a cell is skipped only when that bound is >= 1.0 or strictly above the current 5th
+// best, so no candidate (nor a tie on d2, which is broken by the lower logical index) is lost.
+// Sorted 5-list of packed candidates (float bits of d2) << 32 | logical index: d2 >= 0, so the
+// unsigned 64-bit order is the (d2, index) order.  Empty entries are ~0.
+struct Knn5 {
+  unsigned long long k[5];
+};
+constexpr unsigned long long kEmptyCand = ~0ull;
+
+__device__ __forceinline__ float axis_gap(float q, int cell) {
+  const float lo = 0.5f * (float)cell, hi = lo + 0.5f;   // exact
+  return q < lo ? __fsub_rn(lo, q) : (q > hi ? __fsub_rn(q, hi) : 0.0f);
+}
+
+__device__ __forceinline__ void knn_offer(const float4& pt, float qx, float qy, float qz, float ub, Knn5& k) {
+  // flann::L2_Simple<float>: result += diff*diff over x, y, z in float
+  const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+  const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(pt.w);
+  if (d2 < 1.0f && d2 <= ub && key < k.k[4]) {
+    k.k[4] = key;
+#pragma unroll
+    for (int m = 4; m > 0; --m) {
+      const unsigned long long a = k.k[m - 1], b = k.k[m];
+      k.k[m - 1] = a < b ? a : b; k.k[m] = a < b ? b : a;
+    }
+  }
+}
+
+// `ub`: a known upper bound on the final 5th-best d2 (3e38 when none): larger d2 cannot enter.
+__device__ __forceinline__ void knn_scan_cell(const unsigned long long* __restrict__ tab, const unsigned* __restrict__ hstart,
+                                              const unsigned* __restrict__ hcnt, const float4* __restrict__ sorted,
+                                              unsigned hmask, unsigned gen, int ix, int iy, int iz,
+                                              float qx, float qy, float qz, float ub, Knn5& k) {
+  const float gx = axis_gap(qx, ix), gy = axis_gap(qy, iy), gz = axis_gap(qz, iz);
+  const float dmin = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
+  const unsigned long long key = pack_cell(ix, iy, iz, gen);
+  unsigned slot = hash_cell(key) & hmask;
+  unsigned st = 0, cn = 0;
+  for (;;) {
+    const unsigned long long cur = __ldg(&tab[slot]);
+    if (cur == key) { st = __ldg(&hstart[slot]); cn = __ldg(&hcnt[slot]) & ((1u << kCntBits) - 1u); break; }
+    if ((unsigned)(cur >> 48) != gen) return;  // free slot: the cell is empty
+    slot = (slot + 1) & hmask;
+  }
+  const float4* b = sorted + st;
+  unsigned j = 0;
+  for (; j + 4 <= cn; j += 4) {   // four independent loads in flight
+    const float4 p0 = __ldg(b + j), p1 = __ldg(b + j + 1), p2 = __ldg(b + j + 2), p3 = __ldg(b + j + 3);
+    knn_offer(p0, qx, qy, qz, ub, k); knn_offer(p1, qx, qy, qz, ub, k);
+    knn_offer(p2, qx, qy, qz, ub, k); knn_offer(p3, qx, qy, qz, ub, k);
+  }
+  for (; j < cn; ++j) knn_offer(__ldg(b + j), qx, qy, qz, ub, k);
+}
+
+constexpr int kAssocThreads = 64;
+
+// One thread per edge: transform (A.1: double math, float store), exact 5-NN, line gate
+// (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
+__global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y;
   const OdomState& os = d.ostate[lane_b];
-  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  __shared__ int s_matches;
-  if (threadIdx.x == 0) s_matches = 0;
-  __syncthreads();
   const bool active = force || os.init;
   const int E = os.n_edges;
-  const int e = blockIdx.x * 8 + w;
-  if (active && e < E) {
+  const int t = blockIdx.x * kAssocThreads + threadIdx.x;
+  const int ln = threadIdx.x & 31;
+  bool match = false;
+  if (active && (t - ln) < E) {   // warp-uniform: the shell search below is cooperative
     const WinState& ws = d.wstate[lane_b];
     const double* T = pose_override ? pose_override : os.odom;
-    const float4 c = d.edges[(size_t)lane_b * p.Ecap + e];
+    const bool mine = t < E;
+    // thread -> edge: Morton order from k_edge_order (identity on the stand-alone test path)
+    const int e = (mine && !force) ? d.perm[(size_t)lane_b * p.Ecap + t] : t;
+    const float4 c = mine ? d.edges[(size_t)lane_b * p.Ecap + e] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
-    const int cx = (int)floorf(qx), cy = (int)floorf(qy), cz = (int)floorf(qz);
     const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
-    const unsigned mask = (unsigned)p.Hcap - 1u;
+    const unsigned hmask = (unsigned)p.Hcap - 1u;
     const unsigned long long* tab = d.htab + (size_t)lane_b * p.Hcap;
-    // coalesced bucket probes: lanes 0..26 look up one neighbour cell each
-    unsigned bstart = 0, bcnt = 0;
-    if (ln < 27 && ws.hash_points > 0) {
-      const int dz = ln / 9 - 1, dy = (ln / 3) % 3 - 1, dx = ln % 3 - 1;
-      const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz, gen);
-      unsigned slot = hash_cell(key) & mask;
-      for (;;) {
-        const unsigned long long cur = __ldg(&tab[slot]);
-        if (cur == key) {
-          bstart = d.hstart[(size_t)lane_b * p.Hcap + slot];
-          bcnt = d.hcnt[(size_t)lane_b * p.Hcap + slot] & ((1u << kCntBits) - 1u);
-          break;
-        }
-        if ((unsigned)(cur >> 48) != gen) break;  // free slot: cell is empty
-        slot = (slot + 1) & mask;
-      }
-    }
-    // scan the buckets, all lanes striding over each bucket's contiguous points
+    const unsigned* hstart = d.hstart + (size_t)lane_b * p.Hcap;
+    const unsigned* hcnt = d.hcnt + (size_t)lane_b * p.Hcap;
     const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
-    float bd[5]; int bi[5], bp[5];
+    Knn5 k;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) { bd[k] = 3.0e38f; bi[k] = 0x7fffffff; bp[k] = -1; }
-    unsigned nonempty = __ballot_sync(0xffffffffu, bcnt > 0);
-    while (nonempty) {
-      const int src = __ffs(nonempty) - 1;
-      nonempty &= nonempty - 1;
-      const unsigned st = __shfl_sync(0xffffffffu, bstart, src);
-      const unsigned cn = __shfl_sync(0xffffffffu, bcnt, src);
-      for (unsigned j = ln; j < cn; j += 32) {
-        const float4 pt = __ldg(&sorted[st + j]);
-        // flann::L2_Simple<float>: result += diff*diff over x, y, z in float
-        const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
-        const int idx = __float_as_int(pt.w);
-        if (d2 < 1.0f && cand_less(d2, idx, bd[4], bi[4])) {
-          bd[4] = d2; bi[4] = idx; bp[4] = (int)(st + j);
+    for (int r = 0; r < 5; ++r) k.k[r] = kEmptyCand;
+    const bool searchable = mine && ws.hash_points > 0 && isfinite(qx) && isfinite(qy) && isfinite(qz);
+    const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
+    if (searchable) {
+      knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);   // own cell first: sets the bound
+      for (int ci = 0; ci < 27; ++ci) {
+        const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
+        if (ci != 13) knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
+      }
+    }
+    // Edges whose 5th neighbour is not proven inside the 0.5 m radius: the whole warp scans the
+    // 98 cells of the next shell (lane l takes cells l, l+32, ...), bounded by the owner's
+    // current 5th best, then the per-lane lists are merged by 5 rounds of warp arg-min.
+    unsigned need = __ballot_sync(0xffffffffu, searchable && (unsigned)(k.k[4] >> 32) >= __float_as_uint(0.25f));
+    while (need) {
+      const int owner = __ffs(need) - 1;
+      need &= need - 1;
+      const float jx = __shfl_sync(0xffffffffu, qx, owner), jy = __shfl_sync(0xffffffffu, qy, owner), jz = __shfl_sync(0xffffffffu, qz, owner);
+      const int jcx = __shfl_sync(0xffffffffu, cx, owner), jcy = __shfl_sync(0xffffffffu, cy, owner), jcz = __shfl_sync(0xffffffffu, cz, owner);
+      const unsigned ubb = __shfl_sync(0xffffffffu, (unsigned)(k.k[4] >> 32), owner);
+      const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
+      Knn5 l;
 #pragma unroll
-          for (int k = 4; k > 0; --k)
-            if (cand_less(bd[k], bi[k], bd[k - 1], bi[k - 1])) {
-              const float td = bd[k]; bd[k] = bd[k - 1]; bd[k - 1] = td;
-              const int ti = bi[k]; bi[k] = bi[k - 1]; bi[k - 1] = ti;
-              const int tp = bp[k]; bp[k] = bp[k - 1]; bp[k - 1] = tp;
-            }
+      for (int r = 0; r < 5; ++r) {   // lane 0 inherits the owner's list, the others start empty
+        const unsigned long long v = __shfl_sync(0xffffffffu, k.k[r], owner);
+        l.k[r] = ln == 0 ? v : kEmptyCand;
+      }
+      for (int ci = ln; ci < 125; ci += 32) {
+        const int dz = ci / 25 - 2, dy = (ci / 5) % 5 - 2, dx = ci % 5 - 2;
+        if (abs(dx) == 2 || abs(dy) == 2 || abs(dz) == 2)
+          knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, jcx + dx, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {   // warp arg-min on the 64-bit heads: high word, then low word among ties
+        const unsigned hh = (unsigned)(l.k[0] >> 32), hl = (unsigned)l.k[0];
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hh);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hh == mh ? hl : 0xffffffffu);
+        const int wl = __ffs(__ballot_sync(0xffffffffu, hh == mh && hl == ml)) - 1;
+        if (ln == owner) k.k[r] = ((unsigned long long)mh << 32) | ml;
+        if (ln == wl) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) l.k[q] = l.k[q + 1];
+          l.k[4] = kEmptyCand;
         }
       }
     }
-    // warp merge of the per-lane sorted lists: 5 rounds of arg-min, winner pops its head
-    float nd[5]; int ni[5], npos[5];
+    uint8_t gt = 0;
+    double ev[3] = {0.0, 0.0, 0.0};
+    float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+    if (mine && k.k[4] != kEmptyCand) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
+      gt |= 1;
+      const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
+      float4 nn[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-      float md = bd[0]; int mi = bi[0]; int ml = ln;
+      for (int r = 0; r < 5; ++r) nn[r] = lin[(unsigned)k.k[r]];
+      // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
+      double mx = 0.0, my = 0.0, mz = 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, md, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-        const int ol = __shfl_xor_sync(0xffffffffu, ml, o);
-        if (cand_less(od, oi, md, mi) || (od == md && oi == mi && ol < ml)) { md = od; mi = oi; ml = ol; }
+      for (int r = 0; r < 5; ++r) { mx = ADD(mx, (double)nn[r].x); my = ADD(my, (double)nn[r].y); mz = ADD(mz, (double)nn[r].z); }
+      mx = DIV(mx, 5.0); my = DIV(my, 5.0); mz = DIV(mz, 5.0);
+      double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const double dx = SUB((double)nn[r].x, mx), dy = SUB((double)nn[r].y, my), dz = SUB((double)nn[r].z, mz);
+        c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
+        c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
       }
-      nd[r] = md; ni[r] = mi;
-      npos[r] = __shfl_sync(0xffffffffu, bp[0], ml);
-      if (ln == ml) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { bd[k] = bd[k + 1]; bi[k] = bi[k + 1]; bp[k] = bp[k + 1]; }
-        bd[4] = 3.0e38f; bi[4] = 0x7fffffff; bp[4] = -1;
-      }
+      sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
+      if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
     }
-    if (ln == 0) {
-      uint8_t gt = 0;
-      double ev[3] = {0.0, 0.0, 0.0};
-      float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-      if (ni[4] != 0x7fffffff) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
-        gt |= 1;
-        float4 nn[5];
-#pragma unroll
-        for (int r = 0; r < 5; ++r) nn[r] = sorted[npos[r]];
-        // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
-        double mx = 0.0, my = 0.0, mz = 0.0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) { mx = ADD(mx, (double)nn[r].x); my = ADD(my, (double)nn[r].y); mz = ADD(mz, (double)nn[r].z); }
-        mx = DIV(mx, 5.0); my = DIV(my, 5.0); mz = DIV(mz, 5.0);
-        double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const double dx = SUB((double)nn[r].x, mx), dy = SUB((double)nn[r].y, my), dz = SUB((double)nn[r].z, mz);
-          c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
-          c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
-        }
-        sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
-        if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
-      }
+    if (mine) {
       float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
       blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;
       blk[6] = b.x; blk[7] = b.y; blk[8] = b.z; blk[9] = (gt & 2) ? 1.0f : 0.0f;
-      if (gt & 2) atomicAdd(&s_matches, 1);
-      if (d.gate) {
-        const size_t o = (size_t)lane_b * p.Ecap + e;
-        d.gate[o] = gt;
-        for (int r = 0; r < 5; ++r) {
-          d.knn_idx[o * 5 + r] = ni[r] == 0x7fffffff ? -1 : ni[r];
-          d.knn_d2[o * 5 + r] = ni[r] == 0x7fffffff ? __int_as_float(0x7f800000) : nd[r];
-        }
-        d.eig[o * 3] = ev[0]; d.eig[o * 3 + 1] = ev[1]; d.eig[o * 3 + 2] = ev[2];
-        d.q_world[o] = make_float4(qx, qy, qz, c.w);
+    }
+    match = (gt & 2) != 0;
+    if (mine && d.gate) {
+      const size_t o = (size_t)lane_b * p.Ecap + e;
+      d.gate[o] = gt;
+      for (int r = 0; r < 5; ++r) {
+        d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+        d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
       }
+      d.eig[o * 3] = ev[0]; d.eig[o * 3 + 1] = ev[1]; d.eig[o * 3 + 2] = ev[2];
+      d.q_world[o] = make_float4(qx, qy, qz, c.w);
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && active) {
-    if (s_matches) atomicAdd(&d.diag[lane_b].n_matches[outer_it], s_matches);
-    if (blockIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
-  }
+  const int nm = __popc(__ballot_sync(0xffffffffu, match));
+  if ((threadIdx.x & 31) == 0 && nm) atomicAdd(&d.diag[lane_b].n_matches[outer_it], nm);
+  if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
 }
 #undef MUL
 #undef ADD
@@ -394,8 +508,8 @@ __global__ void __launch_bounds__(256) k_associate(DevBuffers d, int lane0, int 
 #undef DIV
 
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
-  const dim3 g((d.p.Ecap + 7) / 8, lr.nlanes);
-  k_associate<<<g, 256, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override);
+  const dim3 g((d.p.Ecap + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
+  k_associate<<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override);
   return 1;
 }
 
