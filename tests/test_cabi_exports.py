@@ -1,0 +1,46 @@
+"""CPU tests: the C-ABI shared library loads without a GPU and exports every symbol that
+include/liodom_b200.h declares; creating a context without a device fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "liodom_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(liodom_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    from liodom_b200 import build
+    so = build.build()
+    lib = ctypes.CDLL(so)
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_device_means_no_context():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from liodom_b200 import api
+    with pytest.raises(api.LiodomError):
+        api.Context()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under liodom_b200/ may reference it."""
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "liodom_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"^\s*(import|from)\s+oracle\b|liodom_oracle|orc_[a-z]+\(", txt, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad

@@ -151,18 +151,19 @@ def test_threshold_and_break_on_first_smooth_item():
 def test_suppression_window_and_gap_break():
     """After picking p, p+-1..5 are suppressed until a consecutive gap^2 > 0.05 (:280-310)."""
     n = 400
-    ring = _ring_line(n, step=0.05)          # gap^2 = 0.0025: suppression spreads the full +-5
-    ring[200, 2] += 1.0
+    ring = _ring_line(n, step=0.05)
+    ring[:, 2] += np.abs(np.arange(n) - 200).astype(np.float32) * 0.05   # a "V": corner at 200, gaps^2 = 0.005
     o = _extract_single_ring(ring)
     sel = sorted(o["idx"][o["ring"] == 0])
     assert 200 in sel
-    assert not any(195 <= i <= 205 and i != 200 for i in sel)
-    # with a wide gap right after the spike the forward suppression stops immediately
+    assert not any(195 <= i <= 205 and i != 200 for i in sel)            # the full +-5 window is suppressed
+    # with a wide gap right after the corner the forward suppression stops immediately
     ring2 = ring.copy()
-    ring2[201:, 0] += 0.5                     # gap^2 between 200 and 201 = 0.55^2 > 0.05
+    ring2[201:, 0] += 0.5                     # gap^2 between 200 and 201 > 0.05
     o2 = _extract_single_ring(ring2)
     sel2 = sorted(o2["idx"][o2["ring"] == 0])
-    assert 200 in sel2 and any(201 <= i <= 205 for i in sel2)
+    near = [i for i in sel2 if 190 <= i <= 210]
+    assert len(near) >= 2 and np.diff(near).min() <= 5     # two picks closer than the window: only the gap allows it
     assert sel2 == sorted(np_ref.select_ring(ring2))
 
 
@@ -173,11 +174,12 @@ def test_suppression_persists_across_regions():
     ring = _ring_line(n, step=0.05)
     sector = (n - 10) // 8
     last = sector - 1 + 5                     # last ring index of region 0
-    ring[last, 2] += 2.0                      # strongest spike in region 0 (its key dominates)
-    ring[last + 2, 2] += 0.5                  # a weaker spike just inside region 1
+    ring[:, 2] += np.abs(np.arange(n) - last).astype(np.float32) * 0.05   # "V" corner at the region boundary
     o = _extract_single_ring(ring)
+    keys = o["keys"][:n]
+    assert keys[last + 1] >= 0.1 and keys[last + 2] >= 0.1    # region 1 would pick these on its own ...
     sel = list(o["idx"][o["ring"] == 0])
-    assert last in sel and (last + 2) not in sel
+    assert sel == [last]                                       # ... but region 0's pick suppressed them
     assert sel == np_ref.select_ring(ring)
 
 
