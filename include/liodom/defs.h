@@ -1,0 +1,144 @@
+/* liodom facade — type layer (replaces include/liodom/defs.h:35-39 of the reference).
+ *
+ * The reference builds on pcl::PointXYZI / pcl::PointCloud / Eigen / ros::NodeHandle.  None of
+ * those libraries exists in this image, so this header provides layout-compatible stand-ins in
+ * namespace liodom with the member names the reference code touches (points, width, height,
+ * header, at(col,row), matrix(), translation(), ...).  A build that HAS ROS/PCL/Eigen defines
+ * LIODOM_FACADE_USE_PCL and gets the original typedefs instead. */
+#ifndef INCLUDE_LIODOM_DEFS_H
+#define INCLUDE_LIODOM_DEFS_H
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#ifdef LIODOM_FACADE_USE_PCL
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <Eigen/Dense>
+#include <Eigen/Geometry>
+#include <ros/ros.h>
+#include <std_msgs/Header.h>
+namespace liodom {
+typedef pcl::PointXYZI Point;
+typedef pcl::PointCloud<Point> PointCloud;
+typedef std::chrono::high_resolution_clock Clock;
+typedef Eigen::Isometry3d Isometry3d;
+typedef Eigen::Quaterniond Quaterniond;
+typedef Eigen::Matrix4d Matrix4d;
+typedef std_msgs::Header Header;
+typedef ros::NodeHandle NodeHandle;
+}  // namespace liodom
+#else
+
+namespace liodom {
+
+typedef std::chrono::high_resolution_clock Clock;
+
+struct Time {
+  double secs = 0.0;
+  double toSec() const { return secs; }
+};
+struct Header {          // std_msgs::Header
+  uint32_t seq = 0;
+  Time stamp;
+  std::string frame_id;
+};
+
+/* pcl::PointXYZI memory layout: 4 floats (x, y, z, pad) + intensity + 3 pad = 32 bytes, 16-aligned. */
+struct alignas(16) Point {
+  float x = 0.f, y = 0.f, z = 0.f, _pad0 = 1.f;
+  float intensity = 0.f, _pad1[3] = {0.f, 0.f, 0.f};
+};
+static_assert(sizeof(Point) == 32, "liodom::Point must match pcl::PointXYZI");
+
+struct PointCloud {     // the part of pcl::PointCloud<PointXYZI> the reference uses
+  typedef std::shared_ptr<PointCloud> Ptr;
+  typedef std::shared_ptr<const PointCloud> ConstPtr;
+  std::vector<Point> points;
+  uint32_t width = 0, height = 0;
+  bool is_dense = true;
+  Header header;
+  size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  void clear() { points.clear(); width = height = 0; }
+  void push_back(const Point& p) { points.push_back(p); width = (uint32_t)points.size(); height = 1; }
+  const Point& at(int column, int row) const { return points[(size_t)row * width + column]; }
+  PointCloud& operator+=(const PointCloud& o) {
+    points.insert(points.end(), o.points.begin(), o.points.end());
+    width = (uint32_t)points.size(); height = 1;
+    return *this;
+  }
+};
+
+struct Quaterniond {     // Eigen::Quaterniond accessors
+  double qx = 0, qy = 0, qz = 0, qw = 1;
+  double x() const { return qx; } double y() const { return qy; } double z() const { return qz; } double w() const { return qw; }
+};
+
+struct Matrix4d {        // row-major 4x4
+  double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double& operator()(int r, int c) { return m[r * 4 + c]; }
+  double operator()(int r, int c) const { return m[r * 4 + c]; }
+};
+
+struct Isometry3d {      // the part of Eigen::Isometry3d the reference uses
+  Matrix4d mat;
+  static Isometry3d Identity() { return Isometry3d(); }
+  Matrix4d& matrix() { return mat; }
+  const Matrix4d& matrix() const { return mat; }
+  double operator()(int r, int c) const { return mat(r, c); }
+  Isometry3d operator*(const Isometry3d& o) const {
+    Isometry3d r;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) r.mat(i, j) = mat(i, 0) * o.mat(0, j) + mat(i, 1) * o.mat(1, j) + mat(i, 2) * o.mat(2, j);
+      r.mat(i, 3) = (mat(i, 0) * o.mat(0, 3) + mat(i, 1) * o.mat(1, 3) + mat(i, 2) * o.mat(2, 3)) + mat(i, 3);
+    }
+    return r;
+  }
+  Isometry3d inverse() const {
+    Isometry3d r;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.mat(i, j) = mat(j, i);
+    for (int i = 0; i < 3; ++i) r.mat(i, 3) = (-r.mat(i, 0)) * mat(0, 3) + (-r.mat(i, 1)) * mat(1, 3) + (-r.mat(i, 2)) * mat(2, 3);
+    return r;
+  }
+};
+
+/* Parameter source standing in for ros::NodeHandle's private-parameter lookup
+ * (nh.param(name, out, default), src/params.cc:40-108). */
+class NodeHandle {
+ public:
+  NodeHandle() {}
+  template <typename T> void setParam(const std::string& name, const T& v) { std::ostringstream s; s << v; kv_[name] = s.str(); }
+  void setParam(const std::string& name, bool v) { kv_[name] = v ? "1" : "0"; }
+  template <typename T> bool param(const std::string& name, T& out, const T& def) const {
+    auto it = kv_.find(name);
+    if (it == kv_.end()) { out = def; return false; }
+    std::istringstream s(it->second); s >> out;
+    return true;
+  }
+  bool param(const std::string& name, bool& out, const bool& def) const {
+    auto it = kv_.find(name);
+    if (it == kv_.end()) { out = def; return false; }
+    out = (it->second == "1" || it->second == "true" || it->second == "True");
+    return true;
+  }
+  bool param(const std::string& name, std::string& out, const std::string& def) const {
+    auto it = kv_.find(name);
+    if (it == kv_.end()) { out = def; return false; }
+    out = it->second;
+    return true;
+  }
+ private:
+  std::map<std::string, std::string> kv_;
+};
+
+}  // namespace liodom
+#endif  // LIODOM_FACADE_USE_PCL
+#endif  // INCLUDE_LIODOM_DEFS_H

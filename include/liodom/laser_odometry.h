@@ -1,0 +1,61 @@
+/* liodom::LocalMapManager and liodom::LaserOdometer — worker functor of thread B
+ * (include/liodom/laser_odometry.h:59-123, src/laser_odometry.cc:24-272).  The sliding window,
+ * the voxel-hash association and the Levenberg-Marquardt solve all live on the GPU behind
+ * liodom_lmap_* / liodom_register; Ceres / PCL / FLANN are not used. */
+#ifndef INCLUDE_LIODOM_LASER_ODOMETRY_H
+#define INCLUDE_LIODOM_LASER_ODOMETRY_H
+
+#include <atomic>
+#include <functional>
+
+#include <liodom/params.h>
+#include <liodom/shared_data.h>
+#include <liodom/stats.h>
+
+struct liodom_ctx;
+
+namespace liodom {
+
+class LocalMapManager {
+ public:
+  explicit LocalMapManager(const size_t max_frames);
+  virtual ~LocalMapManager();
+
+  void addPointCloud(const PointCloud::Ptr& pc);
+  size_t getLocalMap(PointCloud::Ptr& map);
+  void setMaxFrames(const size_t max_nframes);
+
+ private:
+  std::shared_ptr<liodom_ctx> ctx_;
+  size_t max_nframes_;
+  size_t frame_cap_ = 0;
+  bool ensureContext(size_t frame_points);
+};
+
+class LaserOdometer {
+ public:
+  explicit LaserOdometer(const NodeHandle& nh);
+  LaserOdometer(const LaserOdometer& o);
+  virtual ~LaserOdometer();
+
+  void operator()(std::atomic<bool>& running);
+
+  /* One popFeatures() iteration (src/laser_odometry.cc:108-266) without the queues. */
+  bool process(const PointCloud::Ptr& feats, const Header& header, Isometry3d* pose_out);
+  /* stands in for publishOdom (src/laser_odometry.cc:395-446): header + odom_ (laser frame) */
+  void setOdomCallback(std::function<void(const Header&, const Isometry3d&)> cb) { odom_cb_ = cb; }
+
+ private:
+  NodeHandle nh_;
+  bool init_;
+  Isometry3d odom_;
+  SharedData* sdata;
+  Stats* stats;
+  Params* params;
+  std::shared_ptr<liodom_ctx> ctx_;
+  std::function<void(const Header&, const Isometry3d&)> odom_cb_;
+  bool ensureContext();
+};
+
+}  // namespace liodom
+#endif  // INCLUDE_LIODOM_LASER_ODOMETRY_H

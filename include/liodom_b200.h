@@ -141,6 +141,10 @@ int liodom_scan_batch(liodom_ctx* ctx, const void* const* pts, const int* n, int
                       int width, int height, int on_device);
 /* poses16_out[batch*16], n_edges_out[batch] (either may be NULL) of the last enqueued scan. */
 int liodom_scan_results(liodom_ctx* ctx, double* poses16_out, int* n_edges_out);
+/* Same for age 0 (last enqueued) or 1 (the scan before it): with two scans in flight the caller
+ * enqueues scan k+1, then collects scan k, so the H2D copy of k+1 overlaps the kernels of k.
+ * Host input buffers must stay valid until the results of their scan have been collected. */
+int liodom_scan_results_of(liodom_ctx* ctx, int age, double* poses16_out, int* n_edges_out);
 /* Diagnostics of the last scan of a lane (map sizes, matches, solver summaries); synchronises. */
 int liodom_scan_diag(liodom_ctx* ctx, int lane, liodom_frame_diag* diag);
 /* Edges of the last scan of a lane (device -> host). */

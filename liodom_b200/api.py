@@ -233,11 +233,13 @@ class Context:
         ns = (ctypes.c_int * self.batch)(*counts)
         self._ck(self.lib.liodom_scan_batch(self.h, p, ns, stride_bytes, width, height, 1 if on_device else 0))
 
-    def results(self):
+    def results(self, age=0):
+        """Poses [batch,4,4] and edge counts of the last enqueued scan (age 0) or the one before (age 1)."""
         poses = np.empty((self.batch, 16))
         ne = np.empty(self.batch, np.int32)
-        self._ck(self.lib.liodom_scan_results(self.h, _p(poses), _p(ne)))
-        self._keep = None
+        self._ck(self.lib.liodom_scan_results_of(self.h, age, _p(poses), _p(ne)))
+        if age == 0:
+            self._keep = None
         return poses.reshape(-1, 4, 4), ne
 
     def scan_diag(self, lane=0):

@@ -55,7 +55,22 @@ def build(force=False, verbose=False):
         raise RuntimeError("CUDA build failed")
     if force or _stale(SO, objs):
         subprocess.check_call(["nvcc"] + ARCH + ["-shared", "-ccbin", "g++", "-o", SO] + objs)
+    build_host(force)
     return SO
+
+
+HOST_SO = os.path.join(HERE, "libliodom_host.so")
+
+
+def build_host(force=False):
+    """The C++ facade (reference class surface over the C ABI); links against the CUDA library."""
+    inc = os.path.join(HERE, "..", "include")
+    src = os.path.join(HERE, "host", "facade.cc")
+    deps = [src, SO] + [os.path.join(inc, "liodom", f) for f in os.listdir(os.path.join(inc, "liodom"))]
+    if force or _stale(HOST_SO, deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-Wall", "-I", inc, "-o", HOST_SO, src,
+                               "-L", HERE, "-lliodom_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return HOST_SO
 
 
 if __name__ == "__main__":

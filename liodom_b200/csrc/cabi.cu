@@ -624,14 +624,19 @@ int liodom_stage_times(liodom_ctx* c, double* ms_out, int* n_calls) {
   return 0;
 }
 
-int liodom_scan_results(liodom_ctx* c, double* poses16_out, int* n_edges_out) {
+int liodom_scan_results_of(liodom_ctx* c, int age, double* poses16_out, int* n_edges_out) {
   if (!c) return LIODOM_E_INVALID;
+  if (age != 0 && age != 1) return fail(c, LIODOM_E_INVALID, "age must be 0 (last enqueued scan) or 1 (the one before)");
   CK(cudaSetDevice(c->device));
-  const int buf = c->cur;
+  const int buf = c->cur ^ age;
   if (c->in_flight[buf]) { CK(cudaEventSynchronize(c->ev_done[buf])); c->in_flight[buf] = false; }
   if (poses16_out) std::memcpy(poses16_out, c->h_poses[buf], sizeof(double) * 16 * c->batch);
   if (n_edges_out) std::memcpy(n_edges_out, c->h_nedges[buf], sizeof(int) * c->batch);
   return 0;
+}
+
+int liodom_scan_results(liodom_ctx* c, double* poses16_out, int* n_edges_out) {
+  return liodom_scan_results_of(c, 0, poses16_out, n_edges_out);
 }
 
 int liodom_scan_diag(liodom_ctx* c, int lane, liodom_frame_diag* diag) {

@@ -1,0 +1,474 @@
+// Host facade of the B200 hot path: the reference's class surface (include/liodom/*.h) on top
+// of the C ABI (include/liodom_b200.h).  Everything numeric happens in libliodom_b200.so; this
+// file is queues, ownership and parameter plumbing.  Errors follow the reference's convention:
+// logged, processing continues.
+#include <liodom/feature_extractor.h>
+#include <liodom/laser_odometry.h>
+#include <liodom/map.h>
+
+#include "../../include/liodom_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+namespace liodom {
+
+static bool verbose() { static const bool v = std::getenv("LIODOM_VERBOSE") != nullptr; return v; }
+#define LIODOM_INFO(...) do { if (verbose()) { std::fprintf(stderr, "[liodom] " __VA_ARGS__); std::fprintf(stderr, "\n"); } } while (0)
+#define LIODOM_ERROR(...) do { std::fprintf(stderr, "[liodom][error] " __VA_ARGS__); std::fprintf(stderr, "\n"); } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Params (src/params.cc:24-110)
+// ---------------------------------------------------------------------------------------------
+Params* Params::pinstance_{nullptr};
+std::mutex Params::params_mutex_;
+
+Params* Params::getInstance() {
+  std::lock_guard<std::mutex> lock(params_mutex_);
+  if (pinstance_ == nullptr) pinstance_ = new Params();
+  return pinstance_;
+}
+
+void Params::readParams(const NodeHandle& nh) {
+  nh.param("min_range", min_range_, 3.0);
+  nh.param("max_range", max_range_, 75.0);
+  nh.param("lidar_type", lidar_type_, 0);
+  nh.param("scan_lines", scan_lines_, 64);
+  nh.param("scan_regions", scan_regions_, 8);
+  nh.param("edges_per_region", edges_per_region_, 10);
+  min_points_per_scan_ = (size_t)(scan_regions_ * edges_per_region_ + 10);
+  nh.param("save_results", save_results_, false);
+  nh.param("save_results_dir", results_dir_, std::string("~/"));
+  nh.param("fixed_frame", fixed_frame_, std::string("odom"));
+  nh.param("base_frame", base_frame_, std::string("base_link"));
+  nh.param("laser_frame", laser_frame_, std::string(""));
+  int pframes = 5;
+  nh.param("prev_frames", pframes, 5);
+  local_map_size_ = (size_t)pframes;
+  nh.param("use_imu", use_imu_, false);
+  nh.param("filter_local_map", filter_local_map_, false);
+  nh.param("mapping", mapping_, false);
+  nh.param("publish_tf", publish_tf_, true);
+  LIODOM_INFO("range [%.2f, %.2f], lidar_type %d, scan_lines %d, regions %d, edges/region %d, window %zu, mapping %d",
+              min_range_, max_range_, lidar_type_, scan_lines_, scan_regions_, edges_per_region_, local_map_size_, (int)mapping_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SharedData (src/shared_data.cc:24-117)
+// ---------------------------------------------------------------------------------------------
+SharedData* SharedData::pinstance_{nullptr};
+std::mutex SharedData::sdata_mutex_;
+
+SharedData* SharedData::getInstance() {
+  std::lock_guard<std::mutex> lock(sdata_mutex_);
+  if (pinstance_ == nullptr) pinstance_ = new SharedData();
+  return pinstance_;
+}
+void SharedData::pushPointCloud(const PointCloud::Ptr& pc_in, const Header& header) {
+  std::lock_guard<std::mutex> lock(pc_mutex_);
+  pc_buf_.push(pc_in); pc_header_.push(header);
+}
+bool SharedData::popPointCloud(PointCloud::Ptr& pc_out, Header& header) {
+  std::lock_guard<std::mutex> lock(pc_mutex_);
+  if (pc_buf_.empty()) return false;
+  pc_out = pc_buf_.front(); pc_buf_.pop();
+  header = pc_header_.front(); pc_header_.pop();
+  return true;
+}
+void SharedData::pushFeatures(const PointCloud::Ptr& feat_in, Header& header) {
+  std::lock_guard<std::mutex> lock(feat_mutex_);
+  feat_buf_.push(feat_in); feat_header_.push(header);
+}
+bool SharedData::popFeatures(PointCloud::Ptr& feat_out, Header& header) {
+  std::lock_guard<std::mutex> lock(feat_mutex_);
+  if (feat_buf_.empty()) return false;
+  feat_out = feat_buf_.front(); feat_buf_.pop();
+  header = feat_header_.front(); feat_header_.pop();
+  return true;
+}
+void SharedData::setLocalMap(const PointCloud::Ptr& map_in) {
+  std::lock_guard<std::mutex> lock(map_mutex_);
+  *local_map_ = *map_in;   // pcl::copyPointCloud: deep copy
+}
+void SharedData::getLocalMap(PointCloud::Ptr& map_out) {
+  std::lock_guard<std::mutex> lock(map_mutex_);
+  *map_out = *local_map_;
+}
+void SharedData::setLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); last_IMU_ori_ = imu_ori; }
+void SharedData::getLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); imu_ori = last_IMU_ori_; }
+
+// ---------------------------------------------------------------------------------------------
+// Stats (src/stats.cc:24-132)
+// ---------------------------------------------------------------------------------------------
+Stats* Stats::pinstance_{nullptr};
+std::mutex Stats::sdata_mutex_;
+
+Stats* Stats::getInstance() {
+  std::lock_guard<std::mutex> lock(sdata_mutex_);
+  if (pinstance_ == nullptr) pinstance_ = new Stats();
+  return pinstance_;
+}
+static double whole_ms(const Clock::time_point& a, const Clock::time_point& b) {
+  return (double)std::chrono::duration_cast<std::chrono::milliseconds>(b - a).count();
+}
+void Stats::addPose(const Matrix4d& pose) { poses_.push_back(pose); }
+void Stats::addFeatureExtractionTime(const Clock::time_point& start, const Clock::time_point& end) { feat_extr_.push_back(whole_ms(start, end)); }
+void Stats::addLaserOdometryTime(const Clock::time_point& start, const Clock::time_point& end) { laser_odom_.push_back(whole_ms(start, end)); }
+void Stats::addNumOfFeats(const size_t& nfeats) { num_of_features_.push_back(nfeats); }
+void Stats::startFrame(const Clock::time_point& start) { std::lock_guard<std::mutex> lock(frame_mutex_); start_times_.push(start); }
+void Stats::stopFrame(const Clock::time_point& stop) {
+  std::lock_guard<std::mutex> lock(frame_mutex_);
+  if (!start_times_.empty()) {
+    const Clock::time_point start = start_times_.front();
+    start_times_.pop();
+    frame_times_.push_back(whole_ms(start, stop));
+  }
+}
+void Stats::clear() {
+  std::lock_guard<std::mutex> lock(frame_mutex_);
+  poses_.clear(); feat_extr_.clear(); laser_odom_.clear(); num_of_features_.clear(); frame_times_.clear();
+  while (!start_times_.empty()) start_times_.pop();
+}
+template <typename V> static void write_column(const std::string& path, const V& v) {
+  std::ofstream f(path.c_str(), std::ios::out | std::ios::trunc);
+  for (size_t i = 0; i < v.size(); ++i) f << v[i] << std::endl;
+}
+void Stats::writeResults(const std::string& dir) {
+  {  // KITTI format: the first three rows of every pose on one line, default stream precision
+    std::ofstream f((dir + "poses.txt").c_str(), std::ios::out | std::ios::trunc);
+    for (size_t k = 0; k < poses_.size(); ++k)
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) {
+          f << poses_[k](i, j);
+          if (i == 2 && j == 3) f << std::endl; else f << " ";
+        }
+  }
+  write_column(dir + "feat_ext_times.txt", feat_extr_);
+  write_column(dir + "laser_odom_times.txt", laser_odom_);
+  write_column(dir + "nfeats.txt", num_of_features_);
+  write_column(dir + "frame_times.txt", frame_times_);
+}
+
+// ---------------------------------------------------------------------------------------------
+// context helpers
+// ---------------------------------------------------------------------------------------------
+static std::shared_ptr<liodom_ctx> make_ctx(const Params* params, int max_points, int prev_frames, int max_received) {
+  liodom_params p;
+  liodom_default_params(&p);
+  p.min_range = params->min_range_; p.max_range = params->max_range_; p.lidar_type = params->lidar_type_;
+  p.scan_lines = params->scan_lines_; p.scan_regions = params->scan_regions_; p.edges_per_region = params->edges_per_region_;
+  p.prev_frames = prev_frames; p.filter_local_map = params->filter_local_map_ ? 1 : 0; p.mapping = params->mapping_ ? 1 : 0;
+  p.max_points = max_points; p.max_received_map = max_received;
+  int device = 0;
+  if (const char* d = std::getenv("LIODOM_DEVICE")) device = std::atoi(d);
+  liodom_ctx* c = nullptr;
+  const int rc = liodom_ctx_create(&p, 1, device, &c);
+  if (rc != LIODOM_OK) {
+    // "Invalid scan lines" / "Incorrect Lidar type" are ROS_ERROR_ONCE in the reference
+    // (src/feature_extractor.cc:150,177): log and carry on without output.
+    LIODOM_ERROR("liodom_ctx_create failed (%d): %s", rc, liodom_last_error(nullptr));
+    return std::shared_ptr<liodom_ctx>();
+  }
+  return std::shared_ptr<liodom_ctx>(c, [](liodom_ctx* q) { liodom_ctx_destroy(q); });
+}
+
+static void cloud_from_xyzi(const float* xyzi, int n, PointCloud* pc) {
+  pc->points.resize((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    Point& q = pc->points[(size_t)i];
+    q.x = xyzi[4 * i]; q.y = xyzi[4 * i + 1]; q.z = xyzi[4 * i + 2]; q.intensity = xyzi[4 * i + 3];
+  }
+  pc->width = (uint32_t)n; pc->height = 1; pc->is_dense = true;
+}
+static void xyzi_from_cloud(const PointCloud& pc, std::vector<float>* out) {
+  out->resize(pc.points.size() * 4);
+  for (size_t i = 0; i < pc.points.size(); ++i) {
+    const Point& q = pc.points[i];
+    (*out)[4 * i] = q.x; (*out)[4 * i + 1] = q.y; (*out)[4 * i + 2] = q.z; (*out)[4 * i + 3] = q.intensity;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FeatureExtractor (src/feature_extractor.cc:24-82)
+// ---------------------------------------------------------------------------------------------
+FeatureExtractor::FeatureExtractor(const NodeHandle& nh)
+    : nh_(nh), sdata(SharedData::getInstance()), stats(Stats::getInstance()), params(Params::getInstance()) {}
+FeatureExtractor::FeatureExtractor(const FeatureExtractor& o)
+    : nh_(o.nh_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), edges_cb_(o.edges_cb_), ctx_points_(o.ctx_points_) {}
+FeatureExtractor::~FeatureExtractor() {}
+
+bool FeatureExtractor::ensureContext(size_t npoints) {
+  if (ctx_ && npoints <= ctx_points_) return true;
+  size_t cap = 131072;
+  while (cap < npoints) cap <<= 1;
+  ctx_ = make_ctx(params, (int)cap, (int)params->local_map_size_, 0);
+  ctx_points_ = ctx_ ? cap : 0;
+  return (bool)ctx_;
+}
+
+bool FeatureExtractor::extract(const PointCloud::Ptr& pc_curr, PointCloud::Ptr& pc_edges) {
+  if (!ensureContext(pc_curr->size())) return false;
+  const int cap = liodom_max_edges(ctx_.get());
+  std::vector<float> edges((size_t)cap * 4);
+  int ne = 0;
+  const int w = params->lidar_type_ == 1 ? (int)pc_curr->width : 0, h = params->lidar_type_ == 1 ? (int)pc_curr->height : 0;
+  const int rc = liodom_extract(ctx_.get(), 0, pc_curr->points.data(), (int)pc_curr->size(), (int)sizeof(Point), w, h,
+                                edges.data(), &ne, nullptr, nullptr, nullptr);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_extract failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
+  cloud_from_xyzi(edges.data(), ne, pc_edges.get());
+  return true;
+}
+
+void FeatureExtractor::operator()(std::atomic<bool>& running) {
+  while (running) {
+    PointCloud::Ptr pc_curr(new PointCloud);
+    Header pc_header;
+    if (sdata->popPointCloud(pc_curr, pc_header)) {
+      PointCloud::Ptr pc_edges(new PointCloud);
+      // The reference starts its timer after splitPointCloud (src/feature_extractor.cc:53-55); split and
+      // extraction are one enqueue here, so the span covers both.
+      const auto start_t = Clock::now();
+      extract(pc_curr, pc_edges);
+      const auto end_t = Clock::now();
+      stats->addFeatureExtractionTime(start_t, end_t);
+      stats->addNumOfFeats(pc_edges->size());
+      if (edges_cb_) edges_cb_(pc_header, pc_edges);
+      sdata->pushFeatures(pc_edges, pc_header);
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(2));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LocalMapManager (src/laser_odometry.cc:24-69)
+// ---------------------------------------------------------------------------------------------
+LocalMapManager::LocalMapManager(const size_t max_frames) : max_nframes_(max_frames) {}
+LocalMapManager::~LocalMapManager() {}
+
+bool LocalMapManager::ensureContext(size_t frame_points) {
+  if (ctx_ && frame_points <= frame_cap_) return true;
+  if (ctx_) { LIODOM_ERROR("LocalMapManager: frame of %zu points exceeds the slab capacity %zu", frame_points, frame_cap_); return false; }
+  // slab capacity = scan_lines * scan_regions * (edges_per_region + 1) of the current Params
+  ctx_ = make_ctx(Params::getInstance(), 2048, (int)std::max<size_t>(max_nframes_, 1), 0);
+  frame_cap_ = ctx_ ? (size_t)liodom_max_edges(ctx_.get()) : 0;
+  return ctx_ && frame_points <= frame_cap_;
+}
+void LocalMapManager::addPointCloud(const PointCloud::Ptr& pc) {
+  if (!ensureContext(pc->size())) return;
+  std::vector<float> buf;
+  xyzi_from_cloud(*pc, &buf);
+  const int rc = liodom_lmap_add(ctx_.get(), 0, buf.data(), (int)pc->size());
+  if (rc != LIODOM_OK) LIODOM_ERROR("liodom_lmap_add failed (%d): %s", rc, liodom_last_error(ctx_.get()));
+}
+size_t LocalMapManager::getLocalMap(PointCloud::Ptr& map) {
+  if (!ctx_) { map->clear(); return 0; }
+  int n = 0, nf = 0;
+  liodom_lmap_get(ctx_.get(), 0, nullptr, 0, &n, &nf);
+  std::vector<float> buf((size_t)std::max(n, 1) * 4);
+  const int rc = liodom_lmap_get(ctx_.get(), 0, buf.data(), n, &n, &nf);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_lmap_get failed (%d): %s", rc, liodom_last_error(ctx_.get())); return 0; }
+  cloud_from_xyzi(buf.data(), n, map.get());
+  return (size_t)nf;
+}
+void LocalMapManager::setMaxFrames(const size_t max_nframes) {
+  max_nframes_ = max_nframes;
+  if (ctx_) {
+    const int rc = liodom_lmap_set_max_frames(ctx_.get(), 0, (int)max_nframes);
+    if (rc != LIODOM_OK) LIODOM_ERROR("liodom_lmap_set_max_frames failed (%d): %s", rc, liodom_last_error(ctx_.get()));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LaserOdometer (src/laser_odometry.cc:71-272)
+// ---------------------------------------------------------------------------------------------
+LaserOdometer::LaserOdometer(const NodeHandle& nh)
+    : nh_(nh), init_(false), odom_(Isometry3d::Identity()), sdata(SharedData::getInstance()), stats(Stats::getInstance()),
+      params(Params::getInstance()) {}
+LaserOdometer::LaserOdometer(const LaserOdometer& o)
+    : nh_(o.nh_), init_(o.init_), odom_(o.odom_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), odom_cb_(o.odom_cb_) {}
+LaserOdometer::~LaserOdometer() {}
+
+bool LaserOdometer::ensureContext() {
+  if (ctx_) return true;
+  ctx_ = make_ctx(params, 2048, (int)params->local_map_size_, params->mapping_ ? (1 << 20) : 0);
+  return (bool)ctx_;
+}
+
+bool LaserOdometer::process(const PointCloud::Ptr& feats, const Header& header, Isometry3d* pose_out) {
+  if (!ensureContext()) return false;
+  if (params->mapping_) {   // computeLocalMap: latest map received from the mapping process (src/laser_odometry.cc:276-278)
+    PointCloud::Ptr rec(new PointCloud);
+    sdata->getLocalMap(rec);
+    std::vector<float> buf;
+    xyzi_from_cloud(*rec, &buf);
+    const int rc = liodom_set_received_map(ctx_.get(), 0, buf.data(), (int)rec->size());
+    if (rc != LIODOM_OK) LIODOM_ERROR("liodom_set_received_map failed (%d): %s", rc, liodom_last_error(ctx_.get()));
+  }
+  std::vector<float> buf;
+  xyzi_from_cloud(*feats, &buf);
+  double pose16[16];
+  liodom_frame_diag diag;
+  const int rc = liodom_register(ctx_.get(), 0, buf.data(), (int)feats->size(), pose16, &diag);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_register failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
+  std::memcpy(odom_.matrix().m, pose16, sizeof(pose16));
+  init_ = true;
+  LIODOM_INFO("frame %u: %d edges, map %d, matches %d/%d", header.seq, diag.n_edges, diag.n_map[0], diag.n_matches[0], diag.n_matches[1]);
+  if (pose_out) *pose_out = odom_;
+  return true;
+}
+
+void LaserOdometer::operator()(std::atomic<bool>& running) {
+  while (running) {
+    PointCloud::Ptr feats(new PointCloud);
+    Header feat_header;
+    if (sdata->popFeatures(feats, feat_header)) {
+      const bool first = !init_;
+      const auto start_t = Clock::now();
+      Isometry3d pose;
+      const bool ok = process(feats, feat_header, &pose);
+      const auto end_t = Clock::now();
+      if (ok) {
+        if (!first) stats->addLaserOdometryTime(start_t, end_t);   // the first frame is not timed (src/laser_odometry.cc:108-136)
+        stats->stopFrame(end_t);
+        stats->addPose(odom_.matrix());
+        if (odom_cb_) odom_cb_(feat_header, odom_);
+      }
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(2));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Map (src/map.cc:70-211)
+// ---------------------------------------------------------------------------------------------
+Map::Map(const double xy_size, const double z_size, const double res) : map_(nullptr) {
+  int device = 0;
+  if (const char* d = std::getenv("LIODOM_DEVICE")) device = std::atoi(d);
+  int max_points = 1 << 22;
+  if (const char* d = std::getenv("LIODOM_MAP_MAX_POINTS")) max_points = std::atoi(d);
+  const int rc = liodom_map_create(xy_size, z_size, res, device, max_points, &map_);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_map_create failed (%d): %s", rc, liodom_map_last_error(nullptr)); map_ = nullptr; }
+}
+Map::~Map() { liodom_map_destroy(map_); }
+
+void Map::updateMap(const PointCloud::Ptr& pc_in, const Isometry3d& pose) {
+  if (!map_) return;
+  std::vector<float> buf;
+  xyzi_from_cloud(*pc_in, &buf);
+  const int rc = liodom_map_update(map_, buf.data(), (int)pc_in->size(), pose.matrix().m);
+  if (rc != LIODOM_OK) LIODOM_ERROR("liodom_map_update failed (%d): %s", rc, liodom_map_last_error(map_));
+}
+PointCloud::Ptr Map::getMap() {
+  PointCloud::Ptr out(new PointCloud);
+  if (!map_) return out;
+  int n = 0;
+  liodom_map_size(map_, &n, nullptr);
+  std::vector<float> buf((size_t)std::max(n, 1) * 4);
+  const int rc = liodom_map_get(map_, buf.data(), n, &n);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_map_get failed (%d): %s", rc, liodom_map_last_error(map_)); return out; }
+  cloud_from_xyzi(buf.data(), n, out.get());
+  return out;
+}
+PointCloud::Ptr Map::getLocalMap(const Isometry3d& pose, int cells_xy, int cells_z) {
+  PointCloud::Ptr out(new PointCloud);
+  if (!map_) return out;
+  int n = 0;
+  int rc = liodom_map_get_local(map_, pose.matrix().m, cells_xy, cells_z, nullptr, 0, &n);
+  std::vector<float> buf((size_t)std::max(n, 1) * 4);
+  if (rc == LIODOM_OK && n > 0) rc = liodom_map_get_local(map_, pose.matrix().m, cells_xy, cells_z, buf.data(), n, &n);
+  if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_map_get_local failed (%d): %s", rc, liodom_map_last_error(map_)); return out; }
+  cloud_from_xyzi(buf.data(), n, out.get());
+  return out;
+}
+double Map::getMapEntropy() {
+  if (!map_) return 0.0;
+  int n = 0, nc = 0;
+  liodom_map_size(map_, &n, &nc);
+  if (nc == 0 || n == 0) return 0.0;
+  std::vector<int32_t> keys((size_t)nc * 3), counts((size_t)nc);
+  if (liodom_map_cells(map_, keys.data(), counts.data(), nc, &nc) != LIODOM_OK) return 0.0;
+  double h = 0.0;
+  for (int i = 0; i < nc; ++i)
+    if (counts[(size_t)i] > 0) { const double p = counts[(size_t)i] / (double)n; h += p * std::log(p); }
+  return -h;
+}
+
+}  // namespace liodom
+
+// ---------------------------------------------------------------------------------------------
+// Array-driven harness standing in for liodom_node / liodom_mapping_node (src/liodom_node.cc:72-121,
+// src/liodom_mapping_node.cc:45-90): it feeds clouds through SharedData exactly like lidarClb does
+// and runs the two worker functors on their own threads.  C linkage so that tests can call it.
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+struct liodom_host_options {
+  double min_range, max_range;
+  int lidar_type, scan_lines, scan_regions, edges_per_region, prev_frames, mapping;
+  int width, height;   // organised clouds (lidar_type 1)
+  int lockstep;        // 1: wait for each frame's pose before pushing the next cloud (deterministic)
+};
+
+// scans: concatenated float32 x,y,z,intensity; npts[nframes]. poses_out: nframes x 16 (row-major).
+// Returns the number of poses produced, or a negative value on setup failure.
+int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans, const int* npts, int nframes,
+                             double* poses_out, int* nfeats_out, const char* results_dir) {
+  using namespace liodom;
+  NodeHandle nh;
+  nh.setParam("min_range", opt->min_range); nh.setParam("max_range", opt->max_range);
+  nh.setParam("lidar_type", opt->lidar_type); nh.setParam("scan_lines", opt->scan_lines);
+  nh.setParam("scan_regions", opt->scan_regions); nh.setParam("edges_per_region", opt->edges_per_region);
+  nh.setParam("prev_frames", opt->prev_frames); nh.setParam("mapping", opt->mapping != 0);
+  Params::getInstance()->readParams(nh);
+  Stats* stats = Stats::getInstance();
+  stats->clear();
+  SharedData* sdata = SharedData::getInstance();
+  FeatureExtractor fext(nh);
+  LaserOdometer lodom(nh);
+  std::atomic<int> produced(0);
+  std::vector<int> nf((size_t)nframes, 0);
+  fext.setEdgesCallback([&](const Header& h, const PointCloud::Ptr& e) { if ((int)h.seq < nframes) nf[h.seq] = (int)e->size(); });
+  lodom.setOdomCallback([&](const Header& h, const Isometry3d& pose) {
+    if ((int)h.seq < nframes && poses_out) std::memcpy(poses_out + 16 * (size_t)h.seq, pose.matrix().m, sizeof(double) * 16);
+    produced++;
+  });
+  std::atomic<bool> running(true);
+  std::thread fext_thread(fext, std::ref(running));
+  std::thread lodom_thread(lodom, std::ref(running));
+  size_t pos = 0;
+  for (int f = 0; f < nframes; ++f) {   // lidarClb (src/liodom_node.cc:40-55)
+    PointCloud::Ptr pc(new PointCloud);
+    pc->points.resize((size_t)npts[f]);
+    for (int i = 0; i < npts[f]; ++i) {
+      Point& q = pc->points[(size_t)i];
+      const float* s = scans + (pos + (size_t)i) * 4;
+      q.x = s[0]; q.y = s[1]; q.z = s[2]; q.intensity = s[3];
+    }
+    pos += (size_t)npts[f];
+    pc->width = opt->lidar_type == 1 ? (uint32_t)opt->width : (uint32_t)npts[f];
+    pc->height = opt->lidar_type == 1 ? (uint32_t)opt->height : 1;
+    Header h; h.seq = (uint32_t)f; h.stamp.secs = 0.1 * f; h.frame_id = "laser";
+    stats->startFrame(Clock::now());
+    sdata->pushPointCloud(pc, h);
+    if (opt->lockstep) {
+      const auto t0 = Clock::now();
+      while (produced.load() <= f && std::chrono::duration_cast<std::chrono::seconds>(Clock::now() - t0).count() < 30)
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+  }
+  const auto t0 = Clock::now();
+  while (produced.load() < nframes && std::chrono::duration_cast<std::chrono::seconds>(Clock::now() - t0).count() < 60)
+    std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  running = false;
+  fext_thread.join();
+  lodom_thread.join();
+  if (nfeats_out) std::memcpy(nfeats_out, nf.data(), sizeof(int) * (size_t)nframes);
+  if (results_dir && results_dir[0]) stats->writeResults(results_dir);
+  return produced.load();
+}
+
+}  // extern "C"

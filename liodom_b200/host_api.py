@@ -1,0 +1,41 @@
+"""ctypes front-end of the C++ facade harness (libliodom_host.so): runs a sequence of scans
+through FeatureExtractor / LaserOdometer worker threads and the SharedData queues exactly like
+liodom_node does (src/liodom_node.cc:72-121)."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_SO = os.path.join(_HERE, "libliodom_host.so")
+
+
+class HostOptions(ctypes.Structure):
+    _fields_ = [("min_range", ctypes.c_double), ("max_range", ctypes.c_double), ("lidar_type", ctypes.c_int),
+                ("scan_lines", ctypes.c_int), ("scan_regions", ctypes.c_int), ("edges_per_region", ctypes.c_int),
+                ("prev_frames", ctypes.c_int), ("mapping", ctypes.c_int), ("width", ctypes.c_int), ("height", ctypes.c_int),
+                ("lockstep", ctypes.c_int)]
+
+
+def load():
+    if not os.path.exists(HOST_SO):
+        raise RuntimeError("%s not built: run __graft_entry__.build()" % HOST_SO)
+    lib = ctypes.CDLL(HOST_SO)
+    lib.liodom_host_run_sequence.restype = ctypes.c_int
+    return lib
+
+
+def run_sequence(scans, results_dir="", lockstep=True, width=0, height=0, **kw):
+    """-> (poses [n,4,4], nfeats [n], produced). Parameters use the ROS names of the reference."""
+    lib = load()
+    o = HostOptions(kw.get("min_range", 3.0), kw.get("max_range", 75.0), kw.get("lidar_type", 0), kw.get("scan_lines", 64),
+                    kw.get("scan_regions", 8), kw.get("edges_per_region", 10), kw.get("prev_frames", 5), int(kw.get("mapping", 0)),
+                    width, height, 1 if lockstep else 0)
+    npts = np.array([len(s) for s in scans], np.int32)
+    pts = np.ascontiguousarray(np.concatenate(scans)[:, :4], dtype=np.float32)
+    poses = np.zeros((len(scans), 16))
+    nf = np.zeros(len(scans), np.int32)
+    vp = ctypes.c_void_p
+    produced = lib.liodom_host_run_sequence(ctypes.byref(o), pts.ctypes.data_as(vp), npts.ctypes.data_as(vp), len(scans),
+                                            poses.ctypes.data_as(vp), nf.ctypes.data_as(vp), results_dir.encode())
+    return poses.reshape(-1, 4, 4), nf, produced

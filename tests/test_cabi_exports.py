@@ -44,3 +44,17 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(import|from)\s+oracle\b|liodom_oracle|orc_[a-z]+\(", txt, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_facade_library_exports_reference_classes():
+    """libliodom_host.so carries the reference's class surface."""
+    import subprocess
+    from liodom_b200 import build
+    build.build()
+    out = subprocess.run(["nm", "-DC", build.HOST_SO], capture_output=True, text=True).stdout
+    for sym in ("liodom::FeatureExtractor::operator()(std::atomic<bool>&)", "liodom::LaserOdometer::operator()(std::atomic<bool>&)",
+                "liodom::LocalMapManager::addPointCloud(", "liodom::LocalMapManager::getLocalMap(", "liodom::LocalMapManager::setMaxFrames(",
+                "liodom::Map::updateMap(", "liodom::Map::getMap()", "liodom::Map::getLocalMap(", "liodom::Map::getMapEntropy()",
+                "liodom::SharedData::pushPointCloud(", "liodom::SharedData::popFeatures(", "liodom::SharedData::setLocalMap(",
+                "liodom::Params::readParams(", "liodom::Stats::writeResults(", "liodom::Stats::addPose("):
+        assert sym in out, sym
