@@ -54,13 +54,12 @@ def dist_env():
     return rank, world, local
 
 
-def make_sequences(sensor, rank, nseq, nframes):
-    """nseq sequences x nframes scans (float32 [n,4]); seeds are distinct across ranks."""
-    from liodom_b200 import synth
+def make_sequences(sensor, rank, nseq, nframes, world=1):
+    """This rank's shard of the job's world*nseq independent sequences (float32 [n,4] scans)."""
+    from liodom_b200 import sharding, synth
     out = []
-    for s in range(nseq):
-        seed = 1000 + rank * N_SEEDS + s
-        scans, _ = synth.sequence(sensor, seed, nframes)
+    for sid in sharding.shard_sequences(world * nseq, world, rank):
+        scans, _ = synth.sequence(sensor, sharding.seed_of(sid), nframes)
         out.append(scans)
     return out
 
@@ -130,7 +129,7 @@ def run_b200(args):
     nframes = W + K
     nseq = min(B, N_SEEDS)
     t0 = time.time()
-    seqs = make_sequences(args.sensor, rank, nseq, nframes)
+    seqs = make_sequences(args.sensor, rank, nseq, nframes, world)
     gen_s = time.time() - t0
     npts = np.array([[len(seqs[s][f]) for f in range(nframes)] for s in range(nseq)])
     max_points = 131072 if args.sensor == "hdl64" else 1 << 20
@@ -147,12 +146,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    from liodom_b200.sharding import max_over_ranks
 
     # ---------------- device-resident leg (value) -------------------------------------------
     ctx = api.Context(batch=B, device=local, **kw)
