@@ -1,16 +1,17 @@
 // On-device Levenberg-Marquardt on SE(3) for the weighted edge-to-line cost: replaces the
 // Ceres problem of src/laser_odometry.cc:198-228 with the cost of
 // include/liodom/factors.hpp:64-121 (Point2LineFactor), HuberLoss(0.2) and the
-// EigenQuaternionParameterization tangent space.  One CTA per lane runs the whole solve:
-// per-edge residual/Jacobian in FP64, fixed-order shuffle/shared reduction to the 6x6
-// normal equations, trust-region controller (Ceres 1.14 defaults) on
-// thread 0.  Tolerance parity (1e-4 m / 1e-5 rad), so FMA contraction is allowed here.
+// EigenQuaternionParameterization tangent space.  One thread-block cluster per lane runs the
+// whole solve: per-edge residual/Jacobian in FP64, fixed-order shuffle / shared / distributed-
+// shared reduction to the 6x6 normal equations, trust-region controller (Ceres 1.14 defaults,
+// SURVEY.md App. A.5) on thread 0 of the leading CTA.  Tolerance parity (1e-4 m / 1e-5 rad), so FMA contraction is allowed here.
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <float.h>
 
 namespace liodom {
 
-constexpr int kSolveThreads = 512;
+constexpr int kSolveThreads = 256;
 constexpr int kNumAcc = 29;  // 21 (upper H) + 6 (g) + cost + block count
 
 struct LmCtrl {
@@ -226,38 +227,55 @@ __device__ __forceinline__ void block_reduce(double* acc, double* sred /*[warps]
   __syncthreads();
 }
 
-// F32: residual blocks come from k_associate (float records {c,a,b,valid}); otherwise from
-// a caller-provided double array (liodom_solve, tests).
+// One thread-block CLUSTER per lane runs the whole solve.  The residual blocks are strided over
+// the cluster's CTAs; every evaluation ends in a fixed-order reduction (warp shuffle tree ->
+// warps in order -> CTAs in rank order through distributed shared memory), so the result does
+// not depend on scheduling.  CTA 0 / thread 0 is the trust-region controller; its decision
+// (next point + action) is read back by the other CTAs through DSMEM.
+// F32: residual blocks come from k_associate (float records {c,a,b,valid}); otherwise from a
+// caller-provided double array (liodom_solve, tests).
 template <bool F32>
 __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0, int outer_it, const double* cab_in, int n_in,
                                                           double* qt_inout, SolveSummaryDev* sum_out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks(), crank = cluster.block_rank();
   const DevParams& p = d.p;
-  const int lane_b = lane0 + blockIdx.x;
+  const int lane_b = lane0 + (int)(blockIdx.x / C);
   OdomState& os = d.ostate[lane_b];
-  if (F32 && !os.init) return;
-  __shared__ LmCtrl c;
+  if (F32 && !os.init) return;   // uniform over the cluster
+  __shared__ LmCtrl c;                                         // authoritative copy lives in CTA 0
   __shared__ double sred[(kSolveThreads / 32) * kNumAcc];
-  __shared__ double total[kNumAcc];
+  __shared__ double total[kNumAcc];                            // this CTA's partial sums
+  __shared__ double ctot[kNumAcc];                             // cluster totals (CTA 0)
+  __shared__ double bx[8];                                     // evaluation point + action, local copy
   const int n = F32 ? os.n_edges : n_in;
   const float* blocks = d.blocks + (size_t)lane_b * p.Ecap * 10;
   const double min_d = p.min_range, inv_range = 1.0 / (p.max_range - p.min_range);
-  if (threadIdx.x == 0) {
+  if (crank == 0 && threadIdx.x == 0) {
     if (F32) { for (int k = 0; k < 4; ++k) c.x[k] = os.q[k]; for (int k = 0; k < 3; ++k) c.x[4 + k] = os.t[k]; }
     else for (int k = 0; k < 7; ++k) c.x[k] = qt_inout[k];
     c.radius = 1e4; c.decrease_factor = 2.0; c.reuse_diagonal = 0; c.num_invalid = 0; c.first = 1; c.action = 0;
     c.iteration = 0; c.step_is_successful = 1;
     SolveSummaryDev z = {}; c.sum = z;
   }
-  __syncthreads();
+  const LmCtrl* lead = cluster.map_shared_rank(&c, 0);
   for (;;) {
-    const int action = c.action;
+    cluster.sync();   // the controller's decision is visible
+    if (threadIdx.x < 8) {
+      const int action = lead->action;
+      bx[threadIdx.x] = threadIdx.x < 7 ? (action == 0 ? lead->x[threadIdx.x] : lead->xc[threadIdx.x]) : (double)action;
+    }
+    __syncthreads();
+    const int action = (int)bx[7];
     if (action == 2) break;
     double xs[7];
-    for (int k = 0; k < 7; ++k) xs[k] = action == 0 ? c.x[k] : c.xc[k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) xs[k] = bx[k];
     double acc[kNumAcc];
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = (int)crank * blockDim.x + threadIdx.x; i < n; i += (int)C * blockDim.x) {
       double cab[9];
       if (F32) {
         const float* b = blocks + (size_t)i * 10;
@@ -271,16 +289,24 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
       if (action == 0) eval_block<true>(cab, xs, min_d, inv_range, acc);
       else eval_block<false>(cab, xs, min_d, inv_range, acc);
     }
-    __syncthreads();  // everyone has read c.action / c.x before thread 0 rewrites them
     if (action == 0) block_reduce<0, kNumAcc>(acc, sred, total);
     else block_reduce<27, 1>(acc, sred, total);
-    if (threadIdx.x == 0) {
-      if (action == 0) lm_after_jacobian(c, total);
-      else lm_after_cost(c, total[27]);
+    cluster.sync();   // every CTA's partials are ready
+    if (crank == 0) {
+      const int k0 = action == 0 ? 0 : 27, k1 = action == 0 ? kNumAcc : 28;
+      if ((int)threadIdx.x >= k0 && (int)threadIdx.x < k1) {
+        double s = 0.0;
+        for (unsigned r = 0; r < C; ++r) s += cluster.map_shared_rank(total, r)[threadIdx.x];
+        ctot[threadIdx.x] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (action == 0) lm_after_jacobian(c, ctot);
+        else lm_after_cost(c, ctot[27]);
+      }
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (crank == 0 && threadIdx.x == 0) {
     c.sum.iterations = c.iteration;
     c.sum.final_cost = c.x_cost;
     if (F32) {
@@ -299,15 +325,40 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
       if (sum_out) *sum_out = c.sum;
     }
   }
+  cluster.sync();   // nobody leaves while its shared memory may still be read
+}
+
+// Cluster size: as many CTAs per lane as keep the whole grid in one wave (the kernel needs ~200
+// registers per thread, so one 256-thread CTA per SM; 148 SMs).
+static int solve_cluster_size(int nlanes) {
+  int c = 8;
+  while (c > 1 && nlanes * c > 148) c >>= 1;
+  return c;
+}
+
+template <bool F32>
+static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, int nlanes, int outer_it, const double* cab, int n,
+                                double* qt, SolveSummaryDev* sum) {
+  const int C = solve_cluster_size(nlanes);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(nlanes * C));
+  cfg.blockDim = dim3(kSolveThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_solve<F32>, d, lane0, outer_it, cab, n, qt, sum);
 }
 
 int launch_solve(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it) {
-  k_solve<true><<<lr.nlanes, kSolveThreads, 0, s>>>(d, lr.lane0, outer_it, nullptr, 0, nullptr, nullptr);
+  launch_solve_kernel<true>(d, s, lr.lane0, lr.nlanes, outer_it, nullptr, 0, nullptr, nullptr);
   return 1;
 }
 
 int launch_solve_blocks(const DevBuffers& d, cudaStream_t s, int lane, const double* cab, int n, double* qt_inout, SolveSummaryDev* sum) {
-  k_solve<false><<<1, kSolveThreads, 0, s>>>(d, lane, 0, cab, n, qt_inout, sum);
+  launch_solve_kernel<false>(d, s, lane, 1, 0, cab, n, qt_inout, sum);
   return 1;
 }
 
