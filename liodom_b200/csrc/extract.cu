@@ -245,6 +245,24 @@ __device__ __forceinline__ void mark_pick(const RingView& rv, unsigned* bits, in
   __syncwarp();
 }
 
+// Forward suppression of a region's picks beyond its end `hi` (src/feature_extractor.cc:280-294):
+// bit b set <=> ring index hi + b is marked by a pick of this region.  Warp-uniform result.
+__device__ __forceinline__ unsigned region_spill(const RingView& rv, const int* picks, int np, int hi, int ln) {
+  unsigned m = 0;
+  for (int k = ln; k < np; k += 32) {
+    const int idx = picks[k];
+    if (idx + 5 >= hi && hi + 4 < rv.n) {
+      for (int l = 1; l <= 5; ++l) {
+        if (gap2(rv.P[idx + l], rv.P[idx + l - 1]) > 0.05) break;
+        if (idx + l >= hi) m |= 1u << (idx + l - hi);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  return m;
+}
+
 // Greedy selection of one region by one warp: repeated warp-shuffle arg-max over the
 // not-yet-picked items under the total order (smoothness desc, index asc). Equivalent to
 // std::sort + walk of src/feature_extractor.cc:261-312 whenever the sort order is total.
@@ -357,28 +375,35 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
     if (ln == 0) npicks[r] = np;
   }
   __syncthreads();
-  // sequential fix-up (warp 0): replay the picked_ coupling between regions of the ring
+  // The only coupling between the regions of a ring is picked_: a pick within 5 points of the end of
+  // region r suppresses (gap-limited) up to 5 leading points of region r+1.  Each region's spill is a
+  // 5-bit mask; a region has to be re-run only if one of its speculative picks is in the mask of its
+  // (final) predecessor.  Warp 0 walks the regions in order; without clashes this is O(R) checks.
   if (w == 0) {
-    unsigned* tb = stbits;
+    unsigned spill_prev = 0;   // mask of region r-1 over the indices lo_r + b
     for (int r = 0; r < R; ++r) {
       const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
       int np = npicks[r];
-      bool clash = false;
-      for (int k = ln; k < np; k += 32) clash |= bit_get(tb, picks[r * E1 + k]);
-      if (__any_sync(0xffffffffu, clash)) {
-        // a speculative pick was already suppressed by an earlier region: rerun with the true premask
-        for (int i = (lo >> 5) + ln; i <= ((hi - 1) >> 5); i += 32) {
-          unsigned m = 0xffffffffu;
-          if (i == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
-          if (i == ((hi - 1) >> 5)) m &= 0xffffffffu >> (31 - ((hi - 1) & 31));
-          rv.bits[i] = (rv.bits[i] & ~m) | (tb[i] & m);
+      if (spill_prev) {
+        bool clash = false;
+        for (int k = ln; k < np; k += 32) { const int o = picks[r * E1 + k] - lo; clash |= o < 5 && ((spill_prev >> o) & 1u); }
+        if (__any_sync(0xffffffffu, clash)) {
+          // rerun with the true premask: clear the region's bits, set the spilled ones
+          for (int i = (lo >> 5) + ln; i <= ((hi - 1) >> 5); i += 32) {
+            unsigned m = 0xffffffffu;
+            if (i == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+            if (i == ((hi - 1) >> 5)) m &= 0xffffffffu >> (31 - ((hi - 1) & 31));
+            atomicAnd(&rv.bits[i], ~m);
+          }
+          __syncwarp();
+          if (ln < 5 && ((spill_prev >> ln) & 1u) && lo + ln < hi) bit_set(rv.bits, lo + ln);
+          __syncwarp();
+          np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
+          if (ln == 0) npicks[r] = np;
+          __syncwarp();
         }
-        __syncwarp();
-        np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
-        if (ln == 0) npicks[r] = np;
-        __syncwarp();
       }
-      for (int k = 0; k < np; ++k) mark_pick(rv, tb, picks[r * E1 + k], 0, n, ln);
+      spill_prev = region_spill(rv, picks + r * E1, np, hi, ln);
     }
   }
   __syncthreads();
