@@ -109,8 +109,7 @@ static int hash_generation_guard(liodom_ctx* c, unsigned upcoming_builds) {
   c->builds_since_clear += upcoming_builds;
   if (c->builds_since_clear < 4000u) return 0;
   const DevBuffers& d = c->d;
-  CK(cudaMemsetAsync(d.htab, 0, sizeof(unsigned long long) * (size_t)d.p.Hcap * c->batch, c->stream));
-  CK(cudaMemsetAsync(d.hcnt, 0, sizeof(unsigned) * (size_t)d.p.Hcap * c->batch, c->stream));
+  CK(cudaMemsetAsync(d.htab, 0, sizeof(HashEntry) * (size_t)d.p.Hcap * c->batch, c->stream));
   // reset every lane's generation counter and rebuild
   std::vector<WinState> ws(c->batch);
   CK(cudaMemcpyAsync(ws.data(), d.wstate, sizeof(WinState) * c->batch, cudaMemcpyDeviceToHost, c->stream));
@@ -213,8 +212,6 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.sorted, B * p.Mcap));
   CKC(dalloc(c, &d.lin, B * p.Mcap));
   CKC(dalloc(c, &d.htab, B * p.Hcap));
-  CKC(dalloc(c, &d.hcnt, B * p.Hcap));
-  CKC(dalloc(c, &d.hstart, B * p.Hcap));
   CKC(dalloc(c, &d.pt_slot, B * p.Mcap));
   CKC(dalloc(c, &d.pt_rank, B * p.Mcap));
   CKC(dalloc(c, &d.perm, B * p.Ecap));

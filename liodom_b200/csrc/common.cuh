@@ -11,7 +11,7 @@
 //   win          B x S x Ecap float4    sliding window slabs (world frame), S = prev_frames+1
 //   sorted       B x Mcap float4        window points bucketed by 0.5 m voxel (w = logical index)
 //   lin          B x Mcap float4        window (+ received map) in logical order, for neighbour fetches
-//   htab/hcnt/hstart  B x Hcap          open-addressing voxel hash (generation tagged)
+//   htab         B x Hcap x 16 B        open-addressing voxel hash {key, start, count} (generation tagged)
 //   perm         B x Ecap i32           edges in Morton order of their predicted world cell
 //   blocks       B x Ecap x 10 f32      residual blocks {c, a, b, valid}
 #pragma once
@@ -26,6 +26,15 @@ constexpr int kMaxSlots = 64;       // window slabs upper bound (prev_frames + 1
 constexpr int kRingSmemCap = 6144;  // ring points kept in shared memory by k_extract
 constexpr unsigned kGenBits = 12;   // hash generation tag width
 constexpr unsigned kCntBits = 20;
+
+// One slot of the open-addressing voxel hash: packed cell key (generation | iz | iy | ix), first
+// point of the cell's bucket in `sorted`, and (generation << kCntBits) | points in the cell.
+// 16 bytes, so a probe is one 128-bit load.
+struct __align__(16) HashEntry {
+  unsigned long long key;
+  unsigned start;
+  unsigned cnt;
+};
 
 struct DevParams {
   double min_range, max_range;
@@ -112,9 +121,7 @@ struct DevBuffers {
   OdomState* ostate;       // [B]
   float4* sorted;          // [B][Mcap]
   float4* lin;             // [B][Mcap] the same points in logical (window) order
-  unsigned long long* htab;  // [B][Hcap]
-  unsigned* hcnt;          // [B][Hcap]
-  unsigned* hstart;        // [B][Hcap]
+  HashEntry* htab;         // [B][Hcap]
   unsigned* pt_slot;       // [B][Mcap]
   unsigned* pt_rank;       // [B][Mcap]
   int* perm;               // [B][Ecap] Morton-ordered edge indices (thread -> edge) of k_associate

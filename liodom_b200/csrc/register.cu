@@ -68,8 +68,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
   const int npts = ws.hash_points;
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned mask = (unsigned)d.p.Hcap - 1u;
-  unsigned long long* tab = d.htab + (size_t)lane_b * d.p.Hcap;
-  unsigned* cnt = d.hcnt + (size_t)lane_b * d.p.Hcap;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     const float4 pt = win_point(d, lane_b, v, i);
     unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
@@ -78,18 +77,18 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
     unsigned slot = hash_cell(mine) & mask;
     bool owner = false;
     for (;;) {
-      unsigned long long cur = ((volatile unsigned long long*)tab)[slot];
+      unsigned long long cur = *(volatile unsigned long long*)&tab[slot].key;
       if (cur == mine) break;
       if ((unsigned)(cur >> 48) != gen) {  // stale generation: free
-        const unsigned long long prev = atomicCAS(&tab[slot], cur, mine);
+        const unsigned long long prev = atomicCAS(&tab[slot].key, cur, mine);
         if (prev == cur) { owner = true; break; }
         if (prev == mine) break;
         if ((unsigned)(prev >> 48) != gen) continue;  // lost to another stale observer; retry the slot
       }
       slot = (slot + 1) & mask;
     }
-    atomicMax(&cnt[slot], gen << kCntBits);
-    const unsigned rank = atomicAdd(&cnt[slot], 1u) & ((1u << kCntBits) - 1u);
+    atomicMax(&tab[slot].cnt, gen << kCntBits);
+    const unsigned rank = atomicAdd(&tab[slot].cnt, 1u) & ((1u << kCntBits) - 1u);
     *pslot = slot | (owner ? 0x80000000u : 0u);
     d.pt_rank[(size_t)lane_b * d.p.Mcap + i] = rank;
   }
@@ -99,13 +98,12 @@ __global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
   WinState& ws = d.wstate[lane_b];
   const int npts = ws.hash_points;
-  const unsigned* cnt = d.hcnt + (size_t)lane_b * d.p.Hcap;
-  unsigned* start = d.hstart + (size_t)lane_b * d.p.Hcap;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
     if (ps != 0xffffffffu && (ps & 0x80000000u)) {
       const unsigned slot = ps & 0x7fffffffu;
-      start[slot] = (unsigned)atomicAdd(&ws.bump, (int)(cnt[slot] & ((1u << kCntBits) - 1u)));
+      tab[slot].start = (unsigned)atomicAdd(&ws.bump, (int)(tab[slot].cnt & ((1u << kCntBits) - 1u)));
     }
   }
 }
@@ -116,7 +114,7 @@ __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
   if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
   __syncthreads();
   const int npts = d.wstate[lane_b].hash_points;
-  const unsigned* start = d.hstart + (size_t)lane_b * d.p.Hcap;
+  const HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   float4* sorted = d.sorted + (size_t)lane_b * d.p.Mcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
@@ -124,7 +122,7 @@ __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
     d.lin[(size_t)lane_b * d.p.Mcap + i] = pt;
     if (ps == 0xffffffffu) continue;
     pt.w = __int_as_float(i);
-    sorted[start[ps & 0x7fffffffu] + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
+    sorted[tab[ps & 0x7fffffffu].start + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
   }
 }
 
@@ -354,24 +352,33 @@ __device__ __forceinline__ void knn_offer(const float4& pt, float qx, float qy, 
   }
 }
 
-// `ub`: a known upper bound on the final 5th-best d2 (3e38 when none): larger d2 cannot enter.
-__device__ __forceinline__ void knn_scan_cell(const unsigned long long* __restrict__ tab, const unsigned* __restrict__ hstart,
-                                              const unsigned* __restrict__ hcnt, const float4* __restrict__ sorted,
-                                              unsigned hmask, unsigned gen, int ix, int iy, int iz,
-                                              float qx, float qy, float qz, float ub, Knn5& k) {
-  const float gx = axis_gap(qx, ix), gy = axis_gap(qy, iy), gz = axis_gap(qz, iz);
-  const float dmin = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
+// One probe of the voxel hash: {start, count} of the cell's bucket, count 0 if the cell is empty.
+__device__ __forceinline__ uint2 hash_lookup(const HashEntry* __restrict__ tab, unsigned hmask, unsigned gen, int ix, int iy, int iz) {
   const unsigned long long key = pack_cell(ix, iy, iz, gen);
   unsigned slot = hash_cell(key) & hmask;
-  unsigned st = 0, cn = 0;
   for (;;) {
-    const unsigned long long cur = __ldg(&tab[slot]);
-    if (cur == key) { st = __ldg(&hstart[slot]); cn = __ldg(&hcnt[slot]) & ((1u << kCntBits) - 1u); break; }
-    if ((unsigned)(cur >> 48) != gen) return;  // free slot: the cell is empty
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&tab[slot]));   // key (x,y), start (z), count (w)
+    const unsigned long long cur = ((unsigned long long)e.y << 32) | e.x;
+    if (cur == key) return make_uint2(e.z, e.w & ((1u << kCntBits) - 1u));
+    if ((e.y >> 16) != gen) return make_uint2(0u, 0u);  // free slot: the cell is empty
     slot = (slot + 1) & hmask;
   }
-  const float4* b = sorted + st;
+}
+
+__device__ __forceinline__ float cell_min_d2(float qx, float qy, float qz, int ix, int iy, int iz) {
+  const float gx = axis_gap(qx, ix), gy = axis_gap(qy, iy), gz = axis_gap(qz, iz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+}
+
+// `ub`: a known upper bound on the final 5th-best d2 (3e38 when none): larger d2 cannot enter.
+__device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab, const float4* __restrict__ sorted,
+                                              unsigned hmask, unsigned gen, int ix, int iy, int iz,
+                                              float qx, float qy, float qz, float ub, Knn5& k) {
+  const float dmin = cell_min_d2(qx, qy, qz, ix, iy, iz);
+  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
+  const uint2 sc = hash_lookup(tab, hmask, gen, ix, iy, iz);
+  const unsigned cn = sc.y;
+  const float4* b = sorted + sc.x;
   unsigned j = 0;
   for (; j + 4 <= cn; j += 4) {   // four independent loads in flight
     const float4 p0 = __ldg(b + j), p1 = __ldg(b + j + 1), p2 = __ldg(b + j + 2), p3 = __ldg(b + j + 3);
@@ -404,20 +411,21 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
     const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
     const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
     const unsigned hmask = (unsigned)p.Hcap - 1u;
-    const unsigned long long* tab = d.htab + (size_t)lane_b * p.Hcap;
-    const unsigned* hstart = d.hstart + (size_t)lane_b * p.Hcap;
-    const unsigned* hcnt = d.hcnt + (size_t)lane_b * p.Hcap;
+    const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
     const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
     Knn5 k;
 #pragma unroll
     for (int r = 0; r < 5; ++r) k.k[r] = kEmptyCand;
     const bool searchable = mine && ws.hash_points > 0 && isfinite(qx) && isfinite(qy) && isfinite(qz);
     const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
+    // ---- level 1: the 27-cell cube of every edge, own cell first (it sets the pruning bound).
+    // (A cell-major variant — the warp walking the union of its cubes with broadcast loads — was
+    // measured slower: Morton-adjacent edges still need mostly different cells after pruning.)
     if (searchable) {
-      knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);   // own cell first: sets the bound
+      knn_scan_cell(tab, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);   // own cell first: sets the bound
       for (int ci = 0; ci < 27; ++ci) {
         const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
-        if (ci != 13) knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
+        if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
       }
     }
     // Edges whose 5th neighbour is not proven inside the 0.5 m radius: the whole warp scans the
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
       for (int ci = ln; ci < 125; ci += 32) {
         const int dz = ci / 25 - 2, dy = (ci / 5) % 5 - 2, dx = ci % 5 - 2;
         if (abs(dx) == 2 || abs(dy) == 2 || abs(dz) == 2)
-          knn_scan_cell(tab, hstart, hcnt, sorted, hmask, gen, jcx + dx, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
+          knn_scan_cell(tab, sorted, hmask, gen, jcx + dx, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
       }
       __syncwarp();
 #pragma unroll
