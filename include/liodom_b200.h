@@ -161,6 +161,17 @@ long long liodom_launch_count(const liodom_ctx* ctx);
 int liodom_stage_timing(liodom_ctx* ctx, int enable);  /* (re)starts accumulation; synchronises */
 int liodom_stage_times(liodom_ctx* ctx, double* ms_out /*[LIODOM_NUM_STAGES]*/, int* n_calls);
 
+/* ---- point-sharded mode (BASELINE.json config 5: one large scan across the GPUs of a node) -----
+ * Not in the reference (it is single-process CPU).  Extraction shards by ring
+ * (src/feature_extractor.cc:186-252 processes rings independently), registration by edge; the
+ * window and the LM controller are replicated, so every rank returns the same pose.  Collectives
+ * (NCCL, on the context's stream): one all-gather of the edge slots per scan and one all-reduce of
+ * 29 doubles per LM evaluation.  One process per GPU; rank 0 creates the id and distributes it
+ * (e.g. torch.distributed broadcast); every rank then calls liodom_shard_init on its batch-1
+ * context and feeds the SAME scan to liodom_scan_batch.  scan_lines must be a multiple of world. */
+int liodom_shard_unique_id(char id_out[128]);
+int liodom_shard_init(liodom_ctx* ctx, int rank, int world, const char id[128]);
+
 /* ---- Map (src/map.cc:70-189, include/liodom/map.h:94-116) --------------------------- */
 typedef struct liodom_map liodom_map;
 int liodom_map_create(double voxel_xysize, double voxel_zsize, double resolution, int device,

@@ -70,6 +70,15 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(_vp)
 
 
+def shard_unique_id():
+    """128-byte NCCL unique id for the point-sharded mode (call on one rank, broadcast to the others)."""
+    buf = ctypes.create_string_buffer(128)
+    rc = load().liodom_shard_unique_id(buf)
+    if rc != 0:
+        raise LiodomError("liodom_shard_unique_id failed (%d): %s" % (rc, load().liodom_last_error(None).decode()))
+    return buf.raw
+
+
 def _pts(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     assert a.ndim == 2 and a.shape[1] >= 3
@@ -255,6 +264,11 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.liodom_sync(self.h))
+
+    def shard_init(self, rank, world, unique_id):
+        """Join the point-sharded group (batch-1 contexts, one per GPU); unique_id: 128 bytes."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.liodom_shard_init(self.h, int(rank), int(world), buf))
 
     @property
     def stream(self):

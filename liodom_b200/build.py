@@ -16,6 +16,7 @@ UNITS = {
     "register.cu": ["-fmad=false"],
     "solve.cu": [],
     "map.cu": ["-fmad=false"],
+    "shard.cu": [],
     "cabi.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -54,7 +55,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("CUDA build failed")
     if force or _stale(SO, objs):
-        subprocess.check_call(["nvcc"] + ARCH + ["-shared", "-ccbin", "g++", "-o", SO] + objs)
+        subprocess.check_call(["nvcc"] + ARCH + ["-shared", "-ccbin", "g++", "-o", SO] + objs + ["-ldl"])
     build_host(force)
     return SO
 

@@ -46,6 +46,7 @@ struct liodom_ctx {
   double* stage_pose = nullptr; // [12]
   void* h_scratch = nullptr;    // pinned
   size_t h_scratch_bytes = 0;
+  ShardComm shard;              // point-sharded mode (liodom_shard_init); world == 1: off
   // optional per-stage device timing of liodom_scan_batch (bench roofline evidence)
   bool stage_timing = false;
   std::vector<cudaEvent_t> stage_events;  // LIODOM_NUM_STAGES + 1 events per timed call
@@ -221,6 +222,8 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.gate, B * p.Ecap));
   CKC(dalloc(c, &d.eig, B * p.Ecap * 3));
   CKC(dalloc(c, &d.q_world, B * p.Ecap));
+  { unsigned char* q = nullptr; CKC(dalloc(c, &q, B * shard_ctrl_bytes())); d.shard_ctrl = q; }
+  CKC(dalloc(c, &d.shard_acc, B * 32));
   CKC(dalloc(c, &d.diag, B));
   CKC(dalloc(c, &d.poses_out, B * 16));
   CKC(dalloc(c, &c->stage_pts, (size_t)(p.Mcap > p.Ecap ? p.Mcap : p.Ecap)));
@@ -271,6 +274,7 @@ void liodom_ctx_destroy(liodom_ctx* c) {
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
   if (c->h_scratch) cudaFreeHost(c->h_scratch);
+  shard_comm_destroy(&c->shard);
   for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -523,6 +527,59 @@ static int enqueue_register(liodom_ctx* c, const DevBuffers& d, LaneRange lr) {
   return k;
 }
 
+// Point-sharded scan (one lane): ring-sharded extraction + all-gather of the edge slots, replicated
+// prediction / ordering / window, edge-sharded association and solve with a 29-double all-reduce per
+// LM evaluation.
+static int enqueue_scan_sharded(liodom_ctx* c, const DevBuffers& d, int* launches) {
+  const ShardComm* sc = &c->shard;
+  const LaneRange lr{0, 1};
+  const int L = d.p.scan_lines, per = L / sc->world;
+  const size_t slots_per_rank = (size_t)per * d.p.scan_regions * (d.p.edges_per_region + 1);
+  int k = 0, nrc = 0;
+  stage_mark(c);
+  k += launch_split(d, c->stream, lr);
+  stage_mark(c);
+  k += launch_extract_rings(d, c->stream, lr, sc->rank * per, per);
+  nrc |= shard_group_start();
+  nrc |= shard_allgather_bytes(sc, d.slots, slots_per_rank * sizeof(float4), c->stream);
+  nrc |= shard_allgather_bytes(sc, d.slot_idx, slots_per_rank * sizeof(int), c->stream);
+  nrc |= shard_allgather_bytes(sc, d.region_cnt, (size_t)per * d.p.scan_regions * sizeof(int), c->stream);
+  nrc |= shard_group_end();
+  k += launch_compact(d, c->stream, lr);
+  stage_mark(c);
+  k += launch_predict(d, c->stream, lr);
+  for (int it = 0; it < 2; ++it) {
+    k += launch_associate_shard(d, c->stream, 0, it, sc->rank, sc->world);
+    stage_mark(c);
+    k += launch_solve_shard(d, c->stream, 0, it, sc, &nrc);
+    stage_mark(c);
+  }
+  k += launch_window_update(d, c->stream, lr);
+  stage_mark(c);
+  *launches = k;
+  if (nrc != 0) return fail(c, LIODOM_E_CUDA, "NCCL call failed in the point-sharded scan: %s", shard_error_string(nrc));
+  return 0;
+}
+
+int liodom_shard_unique_id(char id_out[128]) {
+  const int rc = shard_unique_id(id_out);
+  if (rc != 0) return fail(nullptr, LIODOM_E_INVALID, "ncclGetUniqueId: %s", shard_error_string(rc));
+  return 0;
+}
+
+int liodom_shard_init(liodom_ctx* c, int rank, int world, const char id[128]) {
+  if (!c || !id) return LIODOM_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (c->batch != 1) return fail(c, LIODOM_E_INVALID, "point-sharded mode needs a batch-1 context");
+  if (world < 1 || rank < 0 || rank >= world) return fail(c, LIODOM_E_INVALID, "bad rank/world (%d/%d)", rank, world);
+  if (c->params.scan_lines % world != 0) return fail(c, LIODOM_E_INVALID, "scan_lines %d is not a multiple of the world size %d", c->params.scan_lines, world);
+  shard_comm_destroy(&c->shard);
+  if (world == 1) return 0;
+  const int rc = shard_comm_init(&c->shard, rank, world, id);
+  if (rc != 0) return fail(c, LIODOM_E_CUDA, "ncclCommInitRank: %s", shard_error_string(rc));
+  return 0;
+}
+
 int liodom_register(liodom_ctx* c, int lane, const float* edges_xyzi, int n_edges, double* pose16_out, liodom_frame_diag* diag) {
   int rc = check_lane(c, lane); if (rc) return rc;
   rc = hash_generation_guard(c, 1); if (rc) return rc;
@@ -578,12 +635,17 @@ int liodom_scan_batch(liodom_ctx* c, const void* const* pts, const int* n, int s
   CK(cudaMemcpyAsync(d.scan, hd, sizeof(ScanDesc) * B, cudaMemcpyHostToDevice, c->stream));
   const LaneRange lr{0, B};
   int k = 0;
-  stage_mark(c);
-  k += launch_split(d, c->stream, lr);
-  stage_mark(c);
-  k += launch_extract(d, c->stream, lr, false);
-  stage_mark(c);
-  k += enqueue_register(c, d, lr);
+  if (c->shard.world > 1) {
+    rc = enqueue_scan_sharded(c, d, &k);
+    if (rc) return rc;
+  } else {
+    stage_mark(c);
+    k += launch_split(d, c->stream, lr);
+    stage_mark(c);
+    k += launch_extract(d, c->stream, lr, false);
+    stage_mark(c);
+    k += enqueue_register(c, d, lr);
+  }
   c->launches += k;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(c->h_poses[buf], d.poses_out, sizeof(double) * 16 * B, cudaMemcpyDeviceToHost, c->stream));

@@ -131,6 +131,8 @@ struct DevBuffers {
   uint8_t* gate;           // [B][Ecap]
   double* eig;             // [B][Ecap][3]
   float4* q_world;         // [B][Ecap]
+  void* shard_ctrl;        // [B] LM controller state of the point-sharded solve (solve.cu)
+  double* shard_acc;       // [B][32] partial / reduced normal equations of the point-sharded solve
   FrameDiagDev* diag;      // [B]
   double* poses_out;       // [B][16]
 };
@@ -151,6 +153,22 @@ int launch_window_update(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_lmap_add(const DevBuffers& d, cudaStream_t s, int lane, const float4* pts_dev, int n);
 int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out);
 int extract_ring_cap(const DevParams& p);
+int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings);
+int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world);
+
+// ---- point-sharded mode (shard.cu, solve.cu) -----------------------------------------------------
+struct ShardComm { void* comm = nullptr; int rank = 0; int world = 1; };
+int shard_unique_id(char out[128]);
+int shard_comm_init(ShardComm* sc, int rank, int world, const char id_bytes[128]);
+void shard_comm_destroy(ShardComm* sc);
+const char* shard_error_string(int rc);
+int shard_allreduce_f64(const ShardComm* sc, double* buf, size_t n, cudaStream_t s);
+int shard_allgather_bytes(const ShardComm* sc, void* buf, size_t bytes_per_rank, cudaStream_t s);
+int shard_group_start();
+int shard_group_end();
+size_t shard_ctrl_bytes();
+int launch_solve_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, const ShardComm* sc, int* nccl_rc);
 
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pack_cell(int ix, int iy, int iz, unsigned gen) {

@@ -287,9 +287,9 @@ __device__ int run_region(const RingView& rv, int lo, int hi, int epr, int* pick
   return np;
 }
 
-__global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys) {
+__global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
   const DevParams& p = d.p;
-  const int lane_b = lane0 + blockIdx.y, ring = blockIdx.x;
+  const int lane_b = lane0 + blockIdx.y, ring = ring0 + blockIdx.x;   // ring0 > 0: ring-sharded extraction
   const int L = p.scan_lines, R = p.scan_regions, epr = p.edges_per_region, E1 = epr + 1;
   const int* roff = d.ring_off + (size_t)lane_b * (L + 1);
   const int off = roff[ring], n = roff[ring + 1] - off;
@@ -479,6 +479,19 @@ int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   return 3;
 }
 
+int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings) {
+  const int ring_cap = extract_ring_cap(d.p);
+  const size_t sm = extract_smem_bytes(d.p, ring_cap);
+  cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_extract<<<dim3(nrings, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, 0, ring0);
+  return 1;
+}
+int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
+  const int LR = d.p.scan_lines * d.p.scan_regions;
+  k_compact<<<lr.nlanes, 1024, (LR + 32) * sizeof(int), s>>>(d, lr.lane0);
+  return 1;
+}
+
 int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys) {
   const int ring_cap = extract_ring_cap(d.p);
   const size_t sm = extract_smem_bytes(d.p, ring_cap);
@@ -487,7 +500,7 @@ int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_
     cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     configured = sm;
   }
-  k_extract<<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0);
+  k_extract<<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0, 0);
   const int LR = d.p.scan_lines * d.p.scan_regions;
   k_compact<<<lr.nlanes, 1024, (LR + 32) * sizeof(int), s>>>(d, lr.lane0);
   return 2;

@@ -392,13 +392,16 @@ constexpr int kAssocThreads = 64;
 
 // One thread per edge: transform (A.1: double math, float store), exact 5-NN, line gate
 // (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
-__global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override) {
+__global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override,
+                                                                 int shard_rank, int shard_world) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y;
   const OdomState& os = d.ostate[lane_b];
   const bool active = force || os.init;
-  const int E = os.n_edges;
-  const int t = blockIdx.x * kAssocThreads + threadIdx.x;
+  // edge-sharded mode: rank g handles the Morton positions [g * share, (g + 1) * share)
+  const int share = shard_world > 1 ? (((os.n_edges + shard_world - 1) / shard_world + 31) & ~31) : 0;
+  const int E = shard_world > 1 ? min(os.n_edges, (shard_rank + 1) * share) : os.n_edges;
+  const int t = shard_rank * share + blockIdx.x * kAssocThreads + threadIdx.x;
   const int ln = threadIdx.x & 31;
   bool match = false;
   if (active && (t - ln) < E) {   // warp-uniform: the shell search below is cooperative
@@ -517,7 +520,13 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
 
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
   const dim3 g((d.p.Ecap + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
-  k_associate<<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override);
+  k_associate<<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
+  return 1;
+}
+int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world) {
+  const int share = ((d.p.Ecap + world - 1) / world + 31) & ~31;
+  const dim3 g((share + kAssocThreads - 1) / kAssocThreads, 1);
+  k_associate<<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
   return 1;
 }
 

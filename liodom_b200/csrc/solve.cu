@@ -227,6 +227,31 @@ __device__ __forceinline__ void block_reduce(double* acc, double* sred /*[warps]
   __syncthreads();
 }
 
+// Result of a solve -> LaserOdometer state: param_q / param_t, odom_ rebuilt from them without
+// renormalising (src/laser_odometry.cc:222-227), solver summary.
+__device__ void solve_commit(const DevBuffers& d, int lane_b, int outer_it, LmCtrl& c) {
+  OdomState& os = d.ostate[lane_b];
+  c.sum.iterations = c.iteration;
+  c.sum.final_cost = c.x_cost;
+  for (int k = 0; k < 4; ++k) os.q[k] = c.x[k];
+  for (int k = 0; k < 3; ++k) os.t[k] = c.x[4 + k];
+  const double x = c.x[0], y = c.x[1], z = c.x[2], w = c.x[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  os.odom[0] = 1 - (tyy + tzz); os.odom[1] = txy - twz; os.odom[2] = txz + twy; os.odom[3] = c.x[4];
+  os.odom[4] = txy + twz; os.odom[5] = 1 - (txx + tzz); os.odom[6] = tyz - twx; os.odom[7] = c.x[5];
+  os.odom[8] = txz - twy; os.odom[9] = tyz + twx; os.odom[10] = 1 - (txx + tyy); os.odom[11] = c.x[6];
+  d.diag[lane_b].solve[outer_it] = c.sum;
+}
+
+__device__ void lm_init(LmCtrl& c, const OdomState& os) {
+  for (int k = 0; k < 4; ++k) c.x[k] = os.q[k];
+  for (int k = 0; k < 3; ++k) c.x[4 + k] = os.t[k];
+  c.radius = 1e4; c.decrease_factor = 2.0; c.reuse_diagonal = 0; c.num_invalid = 0; c.first = 1; c.action = 0;
+  c.iteration = 0; c.step_is_successful = 1;
+  SolveSummaryDev z = {}; c.sum = z;
+}
+
 // One thread-block CLUSTER per lane runs the whole solve.  The residual blocks are strided over
 // the cluster's CTAs; every evaluation ends in a fixed-order reduction (warp shuffle tree ->
 // warps in order -> CTAs in rank order through distributed shared memory), so the result does
@@ -253,11 +278,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
   const float* blocks = d.blocks + (size_t)lane_b * p.Ecap * 10;
   const double min_d = p.min_range, inv_range = 1.0 / (p.max_range - p.min_range);
   if (crank == 0 && threadIdx.x == 0) {
-    if (F32) { for (int k = 0; k < 4; ++k) c.x[k] = os.q[k]; for (int k = 0; k < 3; ++k) c.x[4 + k] = os.t[k]; }
-    else for (int k = 0; k < 7; ++k) c.x[k] = qt_inout[k];
-    c.radius = 1e4; c.decrease_factor = 2.0; c.reuse_diagonal = 0; c.num_invalid = 0; c.first = 1; c.action = 0;
-    c.iteration = 0; c.step_is_successful = 1;
-    SolveSummaryDev z = {}; c.sum = z;
+    lm_init(c, os);
+    if (!F32) for (int k = 0; k < 7; ++k) c.x[k] = qt_inout[k];
   }
   const LmCtrl* lead = cluster.map_shared_rank(&c, 0);
   for (;;) {
@@ -307,20 +329,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
     }
   }
   if (crank == 0 && threadIdx.x == 0) {
-    c.sum.iterations = c.iteration;
-    c.sum.final_cost = c.x_cost;
-    if (F32) {
-      for (int k = 0; k < 4; ++k) os.q[k] = c.x[k];
-      for (int k = 0; k < 3; ++k) os.t[k] = c.x[4 + k];
-      // odom_ rebuilt from param_q / param_t without renormalising (src/laser_odometry.cc:222-227)
-      const double x = c.x[0], y = c.x[1], z = c.x[2], w = c.x[3];
-      const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-      const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
-      os.odom[0] = 1 - (tyy + tzz); os.odom[1] = txy - twz; os.odom[2] = txz + twy; os.odom[3] = c.x[4];
-      os.odom[4] = txy + twz; os.odom[5] = 1 - (txx + tzz); os.odom[6] = tyz - twx; os.odom[7] = c.x[5];
-      os.odom[8] = txz - twy; os.odom[9] = tyz + twx; os.odom[10] = 1 - (txx + tyy); os.odom[11] = c.x[6];
-      d.diag[lane_b].solve[outer_it] = c.sum;
-    } else {
+    if (F32) solve_commit(d, lane_b, outer_it, c);
+    else {
+      c.sum.iterations = c.iteration;
+      c.sum.final_cost = c.x_cost;
       for (int k = 0; k < 7; ++k) qt_inout[k] = c.x[k];
       if (sum_out) *sum_out = c.sum;
     }
@@ -350,6 +362,82 @@ static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, 
   attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, k_solve<F32>, d, lane0, outer_it, cab, n, qt, sum);
+}
+
+// ---- point-sharded solve: evaluation over this rank's edges, all-reduce, replicated controller ----
+constexpr int kShardEvalThreads = 1024;
+constexpr int kShardMaxEvals = 9;   // 1 Jacobian at the start + per iteration (<= 4) a cost and a Jacobian evaluation
+
+size_t shard_ctrl_bytes() { return sizeof(LmCtrl); }
+
+__global__ void k_shard_begin(DevBuffers d, int lane_b) {
+  if (threadIdx.x != 0) return;
+  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
+  const OdomState& os = d.ostate[lane_b];
+  lm_init(c, os);
+  if (!os.init) c.action = 2;   // first frame: no solve
+}
+
+__global__ void __launch_bounds__(kShardEvalThreads) k_shard_eval(DevBuffers d, int lane_b, int rank, int world) {
+  const DevParams& p = d.p;
+  const LmCtrl& c = static_cast<const LmCtrl*>(d.shard_ctrl)[lane_b];
+  const OdomState& os = d.ostate[lane_b];
+  __shared__ double sred[(kShardEvalThreads / 32) * kNumAcc];
+  __shared__ double total[kNumAcc];
+  const int action = c.action;
+  double acc[kNumAcc];
+#pragma unroll
+  for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
+  if (action != 2) {
+    double xs[7];
+    for (int k = 0; k < 7; ++k) xs[k] = action == 0 ? c.x[k] : c.xc[k];
+    const int E = os.n_edges;
+    const int share = ((E + world - 1) / world + 31) & ~31;     // same partition as k_associate
+    const int t1 = min(E, (rank + 1) * share);
+    const float* blocks = d.blocks + (size_t)lane_b * p.Ecap * 10;
+    const int* perm = d.perm + (size_t)lane_b * p.Ecap;
+    const double min_d = p.min_range, inv_range = 1.0 / (p.max_range - p.min_range);
+    for (int t = rank * share + threadIdx.x; t < t1; t += blockDim.x) {
+      const float* b = blocks + (size_t)perm[t] * 10;
+      if (b[9] == 0.0f) continue;
+      double cab[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) cab[k] = (double)b[k];
+      if (action == 0) eval_block<true>(cab, xs, min_d, inv_range, acc);
+      else eval_block<false>(cab, xs, min_d, inv_range, acc);
+    }
+  }
+  block_reduce<0, kNumAcc>(acc, sred, total);
+  if (threadIdx.x < kNumAcc) d.shard_acc[(size_t)lane_b * 32 + threadIdx.x] = total[threadIdx.x];
+}
+
+__global__ void k_shard_ctrl(DevBuffers d, int lane_b) {
+  if (threadIdx.x != 0) return;
+  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
+  const double* acc = d.shard_acc + (size_t)lane_b * 32;
+  if (c.action == 0) lm_after_jacobian(c, acc);
+  else if (c.action == 1) lm_after_cost(c, acc[27]);
+}
+
+__global__ void k_shard_finish(DevBuffers d, int lane_b, int outer_it) {
+  if (threadIdx.x != 0) return;
+  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
+  if (!d.ostate[lane_b].init) return;
+  solve_commit(d, lane_b, outer_it, c);
+  d.diag[lane_b].n_matches[outer_it] = c.sum.num_residual_blocks;   // all ranks' matches (from the reduced count)
+}
+
+int launch_solve_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, const ShardComm* sc, int* nccl_rc) {
+  int k = 0;
+  k_shard_begin<<<1, 32, 0, s>>>(d, lane); ++k;
+  for (int e = 0; e < kShardMaxEvals; ++e) {
+    k_shard_eval<<<1, kShardEvalThreads, 0, s>>>(d, lane, sc->rank, sc->world); ++k;
+    const int rc = shard_allreduce_f64(sc, d.shard_acc + (size_t)lane * 32, kNumAcc, s);
+    if (rc != 0 && nccl_rc) *nccl_rc = rc;
+    k_shard_ctrl<<<1, 32, 0, s>>>(d, lane); ++k;
+  }
+  k_shard_finish<<<1, 32, 0, s>>>(d, lane, outer_it); ++k;
+  return k;
 }
 
 int launch_solve(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it) {
