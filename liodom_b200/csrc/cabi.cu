@@ -44,8 +44,6 @@ struct liodom_ctx {
   double* stage_qt = nullptr;   // [16]
   SolveSummaryDev* stage_sum = nullptr;
   double* stage_pose = nullptr; // [12]
-  void* h_scratch = nullptr;    // pinned
-  size_t h_scratch_bytes = 0;
   ShardComm shard;              // point-sharded mode (liodom_shard_init); world == 1: off
   // optional per-stage device timing of liodom_scan_batch (bench roofline evidence)
   bool stage_timing = false;
@@ -85,15 +83,6 @@ static cudaError_t dalloc(liodom_ctx* c, T** p, size_t count, bool zero = true) 
   if (zero) { e = cudaMemsetAsync(q, 0, count * sizeof(T) + 256, c->stream); if (e != cudaSuccess) return e; }
   *p = static_cast<T*>(q);
   return cudaSuccess;
-}
-
-static int ensure_scratch(liodom_ctx* c, size_t bytes) {
-  if (bytes <= c->h_scratch_bytes) return 0;
-  if (c->h_scratch) cudaFreeHost(c->h_scratch);
-  c->h_scratch = nullptr; c->h_scratch_bytes = 0;
-  CK(cudaMallocHost(&c->h_scratch, bytes));
-  c->h_scratch_bytes = bytes;
-  return 0;
 }
 
 static int ensure_dev_in(liodom_ctx* c, size_t lane_bytes) {
@@ -187,7 +176,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   p.slots = P.prev_frames + 1;
   p.Rcap = P.mapping ? (P.max_received_map > 0 ? P.max_received_map : 1 << 20) : 0;
   p.Mcap = p.slots * p.Ecap + p.Rcap;
-  int h = 1024; while (h < 2 * p.Mcap) h <<= 1;
+  int h = 1024; while (h < p.Mcap + p.Mcap / 8) h <<= 1;   // load factor <= 0.89 even if every point had its own voxel; typically < 0.2
   p.Hcap = h;
   const size_t B = batch, L = P.scan_lines;
   CKC(dalloc(c, &d.scan, B));
@@ -273,7 +262,6 @@ void liodom_ctx_destroy(liodom_ctx* c) {
     if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
-  if (c->h_scratch) cudaFreeHost(c->h_scratch);
   shard_comm_destroy(&c->shard);
   for (cudaEvent_t e : c->stage_events) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -620,10 +608,25 @@ int liodom_scan_batch(liodom_ctx* c, const void* const* pts, const int* n, int s
   ScanDesc* hd = c->h_desc[buf];
   if (!on_device) {
     rc = ensure_dev_in(c, (size_t)c->d.p.Ncap * 32); if (rc) return rc;
-    for (int l = 0; l < B; ++l) {
-      char* dst = static_cast<char*>(c->dev_in[buf]) + (size_t)l * c->dev_in_lane_bytes;
-      if (n[l] > 0) CK(cudaMemcpyAsync(dst, pts[l], (size_t)n[l] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-      hd[l].pts = dst;
+    // Host scans laid out back to back (a batching front-end would do that) go over PCIe as ONE copy
+    // into a packed staging area; otherwise one copy per lane into fixed-pitch slots.
+    bool packed = B > 1 && (stride_bytes & 15) == 0;
+    size_t total = 0;
+    for (int l = 0; l < B && packed; ++l) {
+      if (static_cast<const char*>(pts[l]) != static_cast<const char*>(pts[0]) + total) packed = false;
+      total += (size_t)n[l] * stride_bytes;
+    }
+    if (packed && total <= c->dev_in_bytes) {
+      char* dst = static_cast<char*>(c->dev_in[buf]);
+      if (total > 0) CK(cudaMemcpyAsync(dst, pts[0], total, cudaMemcpyHostToDevice, c->copy_stream));
+      size_t off = 0;
+      for (int l = 0; l < B; ++l) { hd[l].pts = dst + off; off += (size_t)n[l] * stride_bytes; }
+    } else {
+      for (int l = 0; l < B; ++l) {
+        char* dst = static_cast<char*>(c->dev_in[buf]) + (size_t)l * c->dev_in_lane_bytes;
+        if (n[l] > 0) CK(cudaMemcpyAsync(dst, pts[l], (size_t)n[l] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        hd[l].pts = dst;
+      }
     }
     CK(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));

@@ -32,7 +32,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scans, _ = synth.sequence(a.sensor, 1000, a.frames)
-    kw = dict(prev_frames=15, scan_regions=a.scan_regions, max_points=1 << 20, device=local)
+    kw = dict(prev_frames=15, scan_regions=a.scan_regions, max_points=max(32768, 1 << int(np.ceil(np.log2(max(len(s) for s in scans))))), device=local)
     uid = [api.shard_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     single = api.Context(batch=1, **kw)
