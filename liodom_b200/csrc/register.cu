@@ -5,6 +5,7 @@
 // Bit-exact parts (transform, float L2 distances, centroid/scatter/eigen gate) use the
 // explicit *_rn intrinsics and the file is compiled with -fmad=false.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace liodom {
 
@@ -390,10 +391,12 @@ __device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab,
 
 constexpr int kAssocThreads = 64;
 
-// One thread per edge: transform (A.1: double math, float store), exact 5-NN, line gate
+// G threads per edge (G = 1 for large batches: least work; G = 4 when few edges are in flight:
+// shorter critical path): transform (A.1: double math, float store), exact 5-NN, line gate
 // (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
-__global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, int lane0, int outer_it, int force, const double* pose_override,
-                                                                 int shard_rank, int shard_world) {
+template <int G>
+__global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(DevBuffers d, int lane0, int outer_it, int force,
+                                                                              const double* pose_override, int shard_rank, int shard_world) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y;
   const OdomState& os = d.ostate[lane_b];
@@ -401,10 +404,12 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
   // edge-sharded mode: rank g handles the Morton positions [g * share, (g + 1) * share)
   const int share = shard_world > 1 ? (((os.n_edges + shard_world - 1) / shard_world + 31) & ~31) : 0;
   const int E = shard_world > 1 ? min(os.n_edges, (shard_rank + 1) * share) : os.n_edges;
-  const int t = shard_rank * share + blockIdx.x * kAssocThreads + threadIdx.x;
+  const int t = shard_rank * share + (blockIdx.x * kAssocThreads + threadIdx.x) / G;
   const int ln = threadIdx.x & 31;
+  const int gl = ln & (G - 1);                                   // lane inside the edge's group
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
   bool match = false;
-  if (active && (t - ln) < E) {   // warp-uniform: the shell search below is cooperative
+  if (active && (t - ln / G) < E) {   // warp-uniform: the shell search below is cooperative
     const WinState& ws = d.wstate[lane_b];
     const double* T = pose_override ? pose_override : os.odom;
     const bool mine = t < E;
@@ -424,17 +429,50 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
     // ---- level 1: the 27-cell cube of every edge, own cell first (it sets the pruning bound).
     // (A cell-major variant — the warp walking the union of its cubes with broadcast loads — was
     // measured slower: Morton-adjacent edges still need mostly different cells after pruning.)
-    if (searchable) {
-      knn_scan_cell(tab, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);   // own cell first: sets the bound
-      for (int ci = 0; ci < 27; ++ci) {
-        const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
-        if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
+    if (G == 1) {
+      if (searchable) {
+        knn_scan_cell(tab, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);
+        for (int ci = 0; ci < 27; ++ci) {
+          const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
+          if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
+        }
       }
+    } else {
+      // the group strides over the own cell together, shares the tightest 5th-best as a bound, splits
+      // the 26 neighbours round-robin and merges the G sorted lists by 5 rounds of group arg-min
+      if (searchable) {
+        const uint2 sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
+        for (unsigned j = gl; j < sc.y; j += G) knn_offer(__ldg(sorted + sc.x + j), qx, qy, qz, 3.0e38f, k);
+      }
+      const unsigned ubb = __reduce_min_sync(gmask, (unsigned)(k.k[4] >> 32));
+      const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
+      if (searchable)
+        for (int ci = gl; ci < 27; ci += G) {
+          const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
+          if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, ub, k);
+        }
+      __syncwarp(gmask);
+      unsigned long long res[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) {
+        const unsigned hh = (unsigned)(k.k[0] >> 32), hl = (unsigned)k.k[0];
+        const unsigned mh = __reduce_min_sync(gmask, hh);
+        const unsigned ml = __reduce_min_sync(gmask, hh == mh ? hl : 0xffffffffu);
+        const int wl = __ffs(__ballot_sync(gmask, hh == mh && hl == ml)) - 1;
+        res[r] = ((unsigned long long)mh << 32) | ml;
+        if (ln == wl) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) k.k[q] = k.k[q + 1];
+          k.k[4] = kEmptyCand;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 5; ++r) k.k[r] = res[r];   // the merged list, uniform over the group
     }
     // Edges whose 5th neighbour is not proven inside the 0.5 m radius: the whole warp scans the
     // 98 cells of the next shell (lane l takes cells l, l+32, ...), bounded by the owner's
     // current 5th best, then the per-lane lists are merged by 5 rounds of warp arg-min.
-    unsigned need = __ballot_sync(0xffffffffu, searchable && (unsigned)(k.k[4] >> 32) >= __float_as_uint(0.25f));
+    unsigned need = __ballot_sync(0xffffffffu, searchable && gl == 0 && (unsigned)(k.k[4] >> 32) >= __float_as_uint(0.25f));
     while (need) {
       const int owner = __ffs(need) - 1;
       need &= need - 1;
@@ -471,7 +509,7 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
     uint8_t gt = 0;
     double ev[3] = {0.0, 0.0, 0.0};
     float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-    if (mine && k.k[4] != kEmptyCand) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
+    if (mine && gl == 0 && k.k[4] != kEmptyCand) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
       gt |= 1;
       const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
       float4 nn[5];
@@ -492,13 +530,13 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
       sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
       if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
     }
-    if (mine) {
+    if (mine && gl == 0) {
       float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
       blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;
       blk[6] = b.x; blk[7] = b.y; blk[8] = b.z; blk[9] = (gt & 2) ? 1.0f : 0.0f;
     }
     match = (gt & 2) != 0;
-    if (mine && d.gate) {
+    if (mine && gl == 0 && d.gate) {
       const size_t o = (size_t)lane_b * p.Ecap + e;
       d.gate[o] = gt;
       for (int r = 0; r < 5; ++r) {
@@ -518,15 +556,32 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate(DevBuffers d, i
 #undef SUB
 #undef DIV
 
+// 4 threads per edge while the launch would otherwise leave most of the 148 SMs idle
+// (LIODOM_ASSOC_GROUP=1|4 forces a variant; used by the parity tests to cover both.)
+static bool assoc_use_groups(long long edges_in_flight) {
+  if (const char* e = getenv("LIODOM_ASSOC_GROUP")) { if (e[0] == '1') return false; if (e[0] == '4') return true; }
+  return edges_in_flight <= 12 * 5632;
+}
+
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
-  const dim3 g((d.p.Ecap + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
-  k_associate<<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
+  if (assoc_use_groups((long long)d.p.Ecap * lr.nlanes)) {
+    const dim3 g((d.p.Ecap * 4 + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
+    k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
+  } else {
+    const dim3 g((d.p.Ecap + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
+    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
+  }
   return 1;
 }
 int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world) {
   const int share = ((d.p.Ecap + world - 1) / world + 31) & ~31;
-  const dim3 g((share + kAssocThreads - 1) / kAssocThreads, 1);
-  k_associate<<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
+  if (assoc_use_groups(share)) {
+    const dim3 g((share * 4 + kAssocThreads - 1) / kAssocThreads, 1);
+    k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
+  } else {
+    const dim3 g((share + kAssocThreads - 1) / kAssocThreads, 1);
+    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
+  }
   return 1;
 }
 

@@ -81,7 +81,10 @@ def _teacher_forced_associate(ctx, edges_seq, gt, K):
     return nchecked
 
 
-def test_associate_teacher_forced_c1(cuda_lib):
+@pytest.mark.parametrize("group", ["1", "4"])
+def test_associate_teacher_forced_c1(cuda_lib, group, monkeypatch):
+    """Both kernel variants (1 or 4 threads per edge; picked by the number of edges in flight)."""
+    monkeypatch.setenv("LIODOM_ASSOC_GROUP", group)
     scans, gt = get_sequence("hdl64", 1000, 5)
     op = oracle.make_params(prev_frames=15)
     edges_seq = _edges_of(op, scans)
@@ -216,7 +219,9 @@ def _run_teacher_forced(sensor, seed, nframes, okw, gkw, max_points, traj=0, wid
     return worst
 
 
-def test_register_teacher_forced_c1(cuda_lib):
+@pytest.mark.parametrize("group", ["1", "4"])
+def test_register_teacher_forced_c1(cuda_lib, group, monkeypatch):
+    monkeypatch.setenv("LIODOM_ASSOC_GROUP", group)
     w = _run_teacher_forced("hdl64", 1000, 20, dict(prev_frames=15), dict(prev_frames=15), 131072)
     print("worst teacher-forced pose error C1: %.3g m %.3g rad" % w)
 
