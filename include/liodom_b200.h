@@ -90,6 +90,13 @@ int liodom_lmap_clear(liodom_ctx* ctx, int lane);
 /* SharedData::setLocalMap (src/shared_data.cc:91-96): received local map, mapping=1. */
 int liodom_set_received_map(liodom_ctx* ctx, int lane, const float* xyzi, int n);
 
+/* Device-side hand-off of the same cloud: liodom_received_map_buffer gives the lane's device buffer
+ * (capacity in points), a producer fills it (liodom_map_get_local_device), liodom_commit_received_map
+ * sets its size and rebuilds the voxel hash.  Replaces the ROS hop map_local -> mapClb ->
+ * SharedData::setLocalMap (src/liodom_node.cc:57-64) when both processes' work lives on one GPU. */
+int liodom_received_map_buffer(liodom_ctx* ctx, int lane, void** dev_xyzi, int* cap);
+int liodom_commit_received_map(liodom_ctx* ctx, int lane, int n);
+
 /* ---- LaserOdometer ---------------------------------------------------------------- */
 int liodom_odom_reset(liodom_ctx* ctx, int lane);
 int liodom_odom_set_pose(liodom_ctx* ctx, int lane, const double* odom16, const double* prev_odom16);
@@ -184,6 +191,9 @@ int liodom_map_get(liodom_map* m, float* xyzi, int cap, int* n_points);
 int liodom_map_get_local(liodom_map* m, const double* pose16, int cells_xy, int cells_z,
                          float* xyzi, int cap, int* n_points);
 int liodom_map_cells(liodom_map* m, int32_t* keys3, int32_t* counts, int cap, int* n_cells);
+/* getLocalMap with the result left on the device (dev_xyzi: device pointer to cap float4 records). */
+int liodom_map_get_local_device(liodom_map* m, const double* pose16, int cells_xy, int cells_z,
+                                void* dev_xyzi, int cap, int* n_points);
 
 #ifdef __cplusplus
 }

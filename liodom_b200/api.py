@@ -183,6 +183,17 @@ class Context:
         pts = _f4(pts)
         self._ck(self.lib.liodom_set_received_map(self.h, lane, _p(pts), len(pts)))
 
+    def set_received_map_from(self, gmap, pose, cells_xy=2, cells_z=1, lane=0):
+        """Map::getLocalMap -> SharedData::setLocalMap entirely on the device."""
+        buf = _vp()
+        cap = ctypes.c_int()
+        self._ck(self.lib.liodom_received_map_buffer(self.h, lane, ctypes.byref(buf), ctypes.byref(cap)))
+        T = np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
+        n = ctypes.c_int()
+        gmap._ck(self.lib.liodom_map_get_local_device(gmap.h, _p(T), cells_xy, cells_z, buf, cap.value, ctypes.byref(n)))
+        self._ck(self.lib.liodom_commit_received_map(self.h, lane, n.value))
+        return n.value
+
     # ---- LaserOdometer --------------------------------------------------------------------
     def reset(self, lane=0):
         self._ck(self.lib.liodom_odom_reset(self.h, lane))

@@ -427,6 +427,27 @@ int liodom_set_received_map(liodom_ctx* c, int lane, const float* xyzi, int n) {
   return 0;
 }
 
+// Device-side variant of liodom_set_received_map: the caller (e.g. liodom_map_get_local_device) writes
+// the cloud straight into the lane's received-map buffer, then commits its size.
+int liodom_received_map_buffer(liodom_ctx* c, int lane, void** dev_xyzi, int* cap) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  if (!c->params.mapping) return fail(c, LIODOM_E_INVALID, "context was created with mapping=0");
+  if (dev_xyzi) *dev_xyzi = c->d.received + (size_t)lane * c->d.p.Rcap;
+  if (cap) *cap = c->d.p.Rcap;
+  return 0;
+}
+
+int liodom_commit_received_map(liodom_ctx* c, int lane, int n) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  if (!c->params.mapping) return fail(c, LIODOM_E_INVALID, "context was created with mapping=0");
+  if (n < 0 || n > c->d.p.Rcap) return fail(c, LIODOM_E_CAPACITY, "received map of %d points exceeds max_received_map %d", n, c->d.p.Rcap);
+  CK(cudaMemcpyAsync(&c->d.wstate[lane].n_received, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  rc = hash_generation_guard(c, 1); if (rc) return rc;
+  c->launches += launch_hash_rebuild(c->d, c->stream, lane);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int liodom_odom_reset(liodom_ctx* c, int lane) {
   int rc = check_lane(c, lane); if (rc) return rc;
   OdomState os; std::memset(&os, 0, sizeof(os));

@@ -670,9 +670,8 @@ int liodom_map_get(liodom_map* c, float* xyzi, int cap, int* n_points) {
 
 // Map::getLocalMap (src/map.cc:141-189).  The key list is host integer arithmetic restated from
 // the reference (translation truncated to int; the z loop bounds use voxel_xysize_ and `int += double`).
-int liodom_map_get_local(liodom_map* c, const double* pose16, int cells_xy, int cells_z, float* xyzi, int cap, int* n_points) {
-  if (!c || !pose16) return mfail(c, LIODOM_E_INVALID, "bad arguments");
-  MCK(cudaSetDevice(c->device));
+// The cloud is gathered on the device into `dev_out` (capacity `cap` points); returns its size.
+static int map_local_to_device(liodom_map* c, const double* pose16, int cells_xy, int cells_z, float4* dev_out, int cap, int* n_points) {
   const MapDev& m = c->m;
   const int x = (int)pose16[3], y = (int)pose16[7], z = (int)pose16[11];
   const int vx = (int)(std::floor(x * m.inv_xy) * m.xy + m.xy_half), vy = (int)(std::floor(y * m.inv_xy) * m.xy + m.xy_half);
@@ -680,8 +679,8 @@ int liodom_map_get_local(liodom_map* c, const double* pose16, int cells_xy, int 
   std::vector<int> keys;
   const int init_x = (int)(vx - cells_xy * m.xy), end_x = (int)(vx + cells_xy * m.xy);
   const int init_y = (int)(vy - cells_xy * m.xy), end_y = (int)(vy + cells_xy * m.xy);
-  for (int i = init_x; i <= end_x; i = (int)(i + m.xy))
-    for (int j = init_y; j <= end_y; j = (int)(j + m.xy)) { keys.push_back(i); keys.push_back(j); keys.push_back(vz); if (keys.size() >= 3 * 4096) break; }
+  for (int i = init_x; i <= end_x && keys.size() < 3 * 4096; i = (int)(i + m.xy))
+    for (int j = init_y; j <= end_y && keys.size() < 3 * 4096; j = (int)(j + m.xy)) { keys.push_back(i); keys.push_back(j); keys.push_back(vz); }
   const int init_z = (int)(vz - cells_z * m.xy), end_z = (int)(vz + cells_z * m.xy);
   for (int i = init_z; i <= end_z && keys.size() < 3 * 4096; i = (int)(i + m.zs)) { keys.push_back(vx); keys.push_back(vy); keys.push_back(i); }
   const int nq = (int)keys.size() / 3;
@@ -695,16 +694,41 @@ int liodom_map_get_local(liodom_map* c, const double* pose16, int cells_xy, int 
   MCK(cudaStreamSynchronize(c->stream));
   c->launches += 2;
   if (n_points) *n_points = total;
+  if (dev_out && total > 0) {
+    if (cap < total) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
+    int blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    k_map_gather<<<blocks, 256, 0, c->stream>>>(m.pool[c->cur], c->q_off, c->q_pre, nq, total, dev_out);
+    c->launches += 1;
+    MCK(cudaGetLastError());
+    MCK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int liodom_map_get_local(liodom_map* c, const double* pose16, int cells_xy, int cells_z, float* xyzi, int cap, int* n_points) {
+  if (!c || !pose16) return mfail(c, LIODOM_E_INVALID, "bad arguments");
+  MCK(cudaSetDevice(c->device));
+  int total = 0;
+  int rc = map_local_to_device(c, pose16, cells_xy, cells_z, nullptr, 0, &total);
+  if (rc) return rc;
+  if (n_points) *n_points = total;
   if (xyzi && total > 0) {
     if (cap < total) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
-    if (total > m.cap_points) return mfail(c, LIODOM_E_CAPACITY, "local map of %d points exceeds max_points (duplicated centre cell)", total);
-    int blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    k_map_gather<<<blocks, 256, 0, c->stream>>>(m.pool[c->cur], c->q_off, c->q_pre, nq, total, c->gather_out);
-    c->launches += 1;
+    if (total > c->m.cap_points) return mfail(c, LIODOM_E_CAPACITY, "local map of %d points exceeds max_points (duplicated centre cell)", total);
+    rc = map_local_to_device(c, pose16, cells_xy, cells_z, c->gather_out, c->m.cap_points, &total);
+    if (rc) return rc;
     MCK(cudaMemcpyAsync(xyzi, c->gather_out, (size_t)total * 16, cudaMemcpyDeviceToHost, c->stream));
     MCK(cudaStreamSynchronize(c->stream));
   }
   return 0;
+}
+
+// Same, but the cloud stays on the device (`dev_xyzi`: device pointer, e.g. the buffer returned by
+// liodom_received_map_buffer): the map -> odometry feedback of mapping=1 without a host round trip.
+int liodom_map_get_local_device(liodom_map* c, const double* pose16, int cells_xy, int cells_z, void* dev_xyzi, int cap, int* n_points) {
+  if (!c || !pose16 || !dev_xyzi) return mfail(c, LIODOM_E_INVALID, "bad arguments");
+  MCK(cudaSetDevice(c->device));
+  return map_local_to_device(c, pose16, cells_xy, cells_z, static_cast<float4*>(dev_xyzi), cap, n_points);
 }
 
 int liodom_map_cells(liodom_map* c, int32_t* keys3, int32_t* counts, int cap, int* n_cells) {

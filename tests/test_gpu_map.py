@@ -84,3 +84,49 @@ def test_map_errors(cuda_lib):
     with pytest.raises(api.LiodomError):
         gm.update(np.random.default_rng(0).normal(size=(5000, 4)).astype(np.float32) * 30, np.eye(4))
     gm.close()
+
+
+def test_mapping_feedback_loop(cuda_lib):
+    """mapping:=true (launch/liodom.launch:39-57): per frame the odometry pose feeds Map::updateMap,
+    Map::getLocalMap feeds the next frame's kNN target (src/laser_odometry.cc:276-278,312-314).  GPU:
+    the local map goes map -> odometry on the device; oracle: the same loop on the CPU.  Teacher-forced
+    per frame (the oracle's state is loaded into the GPU lane), so poses must agree to 1e-4 m / 1e-5 rad
+    and both the window + received-map sizes and the maps must match."""
+    from conftest import pose_err
+    scans, _ = get_sequence("hdl64_small", 1000, 8)
+    op = oracle.make_params(prev_frames=5, mapping=1)
+    ctx = api.Context(prev_frames=5, mapping=1, max_points=32768, max_received_map=1 << 18)
+    odo = oracle.Odometer(op)
+    gm, om = api.Map(30.0, 35.0, 0.4, max_points=1 << 19), oracle.Map(30.0, 35.0, 0.4)    # launch/liodom.launch:46-50
+    sizes = []
+    for f, s in enumerate(scans):
+        sp = oracle.split(op, s)
+        edges = oracle.extract(op, sp["rings"], sp["offsets"])["edges"]
+        if f > 0:
+            w, nf = odo.window()
+            ctx.lmap_clear()
+            pos = 0
+            for n in sizes:
+                ctx.lmap_add(w[pos:pos + n])
+                pos += n
+            o_odom, o_prev = odo.get_pose()
+            ctx.set_pose(o_odom, o_prev)
+        opose, od = odo.process(edges)
+        gpose, gd = ctx.register(edges)
+        if f > 0:
+            assert gd.n_map[0] == od.n_map[0] and gd.n_map[0] > sum(sizes)      # window + received map
+        dt, dr = pose_err(gpose, opose)
+        assert dt < 1e-4 and dr < 1e-5, (f, dt, dr)
+        sizes.append(len(edges))
+        if len(sizes) > 5:
+            sizes.pop(0)
+        # mapping process: both sides integrate the ORACLE pose so that the maps stay comparable
+        gm.update(edges, opose)
+        om.update(edges, opose)
+        loc = om.get_local_map(opose, 3, 2)
+        odo.set_received_map(loc)
+        n = ctx.set_received_map_from(gm, opose, 3, 2)
+        assert n == len(loc)
+    _same(gm, om, opose, (3, 2))
+    ctx.close()
+    gm.close()

@@ -238,6 +238,30 @@ def test_register_teacher_forced_c3_stress(cuda_lib):
     _run_teacher_forced("hdl64", 1003, 6, kw, kw, 131072)
 
 
+def test_register_teacher_forced_c2_ouster(cuda_lib):
+    """C2: organised OS1-128-shaped clouds (launch/liodom_ouster.launch params with scan_lines=128)."""
+    from liodom_b200 import synth
+    w, h = synth.sensor_shape("os1_128")
+    kw = dict(lidar_type=1, scan_lines=128, prev_frames=15)
+    worst = _run_teacher_forced("os1_128", 1000, 5, kw, kw, 262144, width=w, height=h)
+    print("worst teacher-forced pose error C2: %.3g m %.3g rad" % worst)
+
+
+def test_whole_path_1m_point_scan(cuda_lib):
+    """C5: 1M-point scans (64 x 15,625) with scan_regions=64 through the whole path, free-running."""
+    scans, _ = get_sequence("hdl64_1m", 1000, 3)
+    op = oracle.make_params(prev_frames=15, scan_regions=64)
+    oposes, _, _ = oracle.run_sequence(op, scans)
+    ctx = api.Context(prev_frames=15, scan_regions=64, max_points=1 << 20)
+    for f, s in enumerate(scans):
+        ctx.scan_batch([s])
+        p, ne = ctx.results()
+        assert ne[0] > 30000
+        dt, dr = pose_err(p[0], oposes[f])
+        assert dt < 1e-4 and dr < 1e-5, (f, dt, dr)
+    ctx.close()
+
+
 def test_free_running_ate_c1(cuda_lib):
     """Free-running whole path (host scans -> poses) vs the oracle's free run: ATE within 1%."""
     scans, gt = get_sequence("hdl64", 1000, 30)
