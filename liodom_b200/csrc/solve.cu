@@ -124,7 +124,12 @@ __device__ void lm_after_jacobian(LmCtrl& c, const double* acc) {
   lm_try_step(c);
 }
 
-__device__ void lm_after_cost(LmCtrl& c, double candidate_cost) {
+// `acc` holds cost AND normal equations at the candidate xc: the Jacobian is evaluated in the same pass
+// as the cost (speculating on acceptance, which is the common case), so an accepted step needs no
+// second pass over the residual blocks.  Rejected steps simply discard it.  The counters keep Ceres'
+// meaning (a Jacobian evaluation is counted only when the step is accepted).
+__device__ void lm_after_cost(LmCtrl& c, const double* acc) {
+  double candidate_cost = acc[27];
   c.sum.cost_evals++;
   if (!isfinite(candidate_cost)) candidate_cost = c.x_cost;
   double sn = 0.0; for (int k = 0; k < 7; ++k) sn += (c.x[k] - c.xc[k]) * (c.x[k] - c.xc[k]);
@@ -140,7 +145,7 @@ __device__ void lm_after_cost(LmCtrl& c, double candidate_cost) {
     const double u = 2.0 * rel - 1.0;
     c.radius = fmin(1e16, c.radius / fmax(1.0 / 3.0, 1.0 - u * u * u));
     c.decrease_factor = 2.0; c.reuse_diagonal = 0; c.step_is_successful = 1;
-    c.action = 0;
+    lm_after_jacobian(c, acc);   // gradient / Jacobian at the new point, then the next trust-region step
     return;
   }
   c.step_is_successful = 0;  // HandleUnsuccessfulStep
@@ -308,15 +313,12 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
 #pragma unroll
         for (int k = 0; k < 9; ++k) cab[k] = cab_in[(size_t)i * 9 + k];
       }
-      if (action == 0) eval_block<true>(cab, xs, min_d, inv_range, acc);
-      else eval_block<false>(cab, xs, min_d, inv_range, acc);
+      eval_block<true>(cab, xs, min_d, inv_range, acc);   // cost and Jacobian in one pass (see lm_after_cost)
     }
-    if (action == 0) block_reduce<0, kNumAcc>(acc, sred, total);
-    else block_reduce<27, 1>(acc, sred, total);
+    block_reduce<0, kNumAcc>(acc, sred, total);
     cluster.sync();   // every CTA's partials are ready
     if (crank == 0) {
-      const int k0 = action == 0 ? 0 : 27, k1 = action == 0 ? kNumAcc : 28;
-      if ((int)threadIdx.x >= k0 && (int)threadIdx.x < k1) {
+      if ((int)threadIdx.x < kNumAcc) {
         double s = 0.0;
         for (unsigned r = 0; r < C; ++r) s += cluster.map_shared_rank(total, r)[threadIdx.x];
         ctot[threadIdx.x] = s;
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
       __syncthreads();
       if (threadIdx.x == 0) {
         if (action == 0) lm_after_jacobian(c, ctot);
-        else lm_after_cost(c, ctot[27]);
+        else lm_after_cost(c, ctot);
       }
     }
   }
@@ -366,7 +368,7 @@ static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, 
 
 // ---- point-sharded solve: evaluation over this rank's edges, all-reduce, replicated controller ----
 constexpr int kShardEvalThreads = 1024;
-constexpr int kShardMaxEvals = 9;   // 1 Jacobian at the start + per iteration (<= 4) a cost and a Jacobian evaluation
+constexpr int kShardMaxEvals = 5;   // the initial evaluation + one (cost + Jacobian) evaluation per iteration (<= 4)
 
 size_t shard_ctrl_bytes() { return sizeof(LmCtrl); }
 
@@ -403,8 +405,7 @@ __global__ void __launch_bounds__(kShardEvalThreads) k_shard_eval(DevBuffers d, 
       double cab[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) cab[k] = (double)b[k];
-      if (action == 0) eval_block<true>(cab, xs, min_d, inv_range, acc);
-      else eval_block<false>(cab, xs, min_d, inv_range, acc);
+      eval_block<true>(cab, xs, min_d, inv_range, acc);
     }
   }
   block_reduce<0, kNumAcc>(acc, sred, total);
@@ -416,7 +417,7 @@ __global__ void k_shard_ctrl(DevBuffers d, int lane_b) {
   LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
   const double* acc = d.shard_acc + (size_t)lane_b * 32;
   if (c.action == 0) lm_after_jacobian(c, acc);
-  else if (c.action == 1) lm_after_cost(c, acc[27]);
+  else if (c.action == 1) lm_after_cost(c, acc);
 }
 
 __global__ void k_shard_finish(DevBuffers d, int lane_b, int outer_it) {
