@@ -66,6 +66,9 @@ struct WinState {
   int hash_points;        // points inserted in the current hash build
   int bump;               // bucket allocator
   int pad;
+  // logical view of the window (oldest frame first), refreshed whenever the window changes:
+  int view_prefix[kMaxSlots + 1];   // first logical index of frame k
+  int view_slab[kMaxSlots];         // slab holding frame k
 };
 
 // LaserOdometer state (src/laser_odometry.cc: odom_, prev_odom_, param_q, param_t, init_).

@@ -12,34 +12,38 @@ namespace liodom {
 // ---------------------------------------------------------------------------------------
 // window addressing
 // ---------------------------------------------------------------------------------------
+// Logical window addressing: frame k (oldest first) lives in slab view_slab[k] and starts at logical
+// index view_prefix[k].  The view is kept in WinState (refreshed by hash_begin, i.e. whenever the
+// window changed) so that kernels only read it.
 struct WinView {
-  int prefix[kMaxSlots + 1];
-  int slab[kMaxSlots];
+  const int* prefix;
+  const int* slab;
   int nframes, total, n_received;
 };
 
 __device__ __forceinline__ void load_win_view(const DevBuffers& d, int lane_b, WinView* v) {
   const WinState& ws = d.wstate[lane_b];
-  int acc = 0;
-  for (int k = 0; k < ws.nframes; ++k) {
-    const int s = (ws.head + k) % d.p.slots;
-    v->slab[k] = s; v->prefix[k] = acc; acc += ws.cnt[s];
-  }
-  v->prefix[ws.nframes] = acc;
-  v->nframes = ws.nframes; v->total = acc;
+  v->prefix = ws.view_prefix; v->slab = ws.view_slab;
+  v->nframes = ws.nframes; v->total = ws.view_prefix[ws.nframes];
   v->n_received = d.p.mapping ? ws.n_received : 0;
 }
 
 __device__ __forceinline__ float4 win_point(const DevBuffers& d, int lane_b, const WinView& v, int i) {
   if (i >= v.total) return d.received[(size_t)lane_b * d.p.Rcap + (i - v.total)];
-  int k = 0;
-  while (i >= v.prefix[k + 1]) ++k;
-  return d.win[((size_t)lane_b * d.p.slots + v.slab[k]) * d.p.Ecap + (i - v.prefix[k])];
+  int lo = 0, hi = v.nframes;   // last frame with prefix <= i
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(v.prefix + mid) <= i) lo = mid; else hi = mid; }
+  return d.win[((size_t)lane_b * d.p.slots + __ldg(v.slab + lo)) * d.p.Ecap + (i - __ldg(v.prefix + lo))];
 }
 
 // Called by exactly one thread after the window changed: start a new hash generation.
 __device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
   WinState& ws = d.wstate[lane_b];
+  int acc = 0;
+  for (int k = 0; k < ws.nframes; ++k) {
+    const int s = (ws.head + k) % d.p.slots;
+    ws.view_slab[k] = s; ws.view_prefix[k] = acc; acc += ws.cnt[s];
+  }
+  ws.view_prefix[ws.nframes] = acc;
   ws.gen = ws.gen + 1u;
   ws.bump = 0;
   ws.hash_points = ws.total + (d.p.mapping ? ws.n_received : 0);
@@ -62,9 +66,8 @@ __device__ __forceinline__ void win_commit(const DevBuffers& d, int lane_b, int 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
-  __shared__ WinView v;
-  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
-  __syncthreads();
+  WinView v;
+  load_win_view(d, lane_b, &v);
   const WinState& ws = d.wstate[lane_b];
   const int npts = ws.hash_points;
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
@@ -111,9 +114,8 @@ __global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
 
 __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
-  __shared__ WinView v;
-  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
-  __syncthreads();
+  WinView v;
+  load_win_view(d, lane_b, &v);
   const int npts = d.wstate[lane_b].hash_points;
   const HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   float4* sorted = d.sorted + (size_t)lane_b * d.p.Mcap;
@@ -650,9 +652,8 @@ int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane) {
 
 // gather the window in logical order (LocalMapManager::getLocalMap)
 __global__ void __launch_bounds__(256) k_lmap_gather(DevBuffers d, int lane_b, float4* out) {
-  __shared__ WinView v;
-  if (threadIdx.x == 0) load_win_view(d, lane_b, &v);
-  __syncthreads();
+  WinView v;
+  load_win_view(d, lane_b, &v);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.total; i += gridDim.x * blockDim.x) out[i] = win_point(d, lane_b, v, i);
 }
 int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out) {
