@@ -203,7 +203,7 @@ __global__ void k_predict(DevBuffers d, int lane0) {
 // one k_associate warp then walk the same / neighbouring hash buckets (broadcast loads, similar
 // trip counts).  Only the thread -> edge assignment changes; outputs stay in edge order.
 // One CTA sorts a chunk of kOrderChunk edges in shared memory (bitonic, 64-bit key|index).
-constexpr int kOrderChunk = 8192;
+constexpr int kOrderChunk = 4096;
 __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
   v &= 0x3ffu;
   v = (v | (v << 16)) & 0x030000ffu;
@@ -239,6 +239,8 @@ __global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
     sk[i] = v;
   }
   __syncthreads();
+  // Thread t owns the pairs t, t + 1024, ...; for j <= 32 both elements of all its pairs (and of its
+  // warp's pairs) stay inside the warp's own 64-element blocks, so those phases need only a warp sync.
   for (int k = 2; k <= np2; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
@@ -247,8 +249,9 @@ __global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
         const bool up = (lo & k) == 0;
         if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
       }
-      __syncthreads();
+      if (j > 32 || (j == 1 && k >= 64)) __syncthreads(); else __syncwarp();
     }
+  __syncthreads();
   int* perm = d.perm + (size_t)lane_b * p.Ecap + base;
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = base + (int)(unsigned)(sk[i] & 0xffffffffull);
 }
