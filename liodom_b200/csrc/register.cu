@@ -203,7 +203,7 @@ __global__ void k_predict(DevBuffers d, int lane0) {
 // one k_associate warp then walk the same / neighbouring hash buckets (broadcast loads, similar
 // trip counts).  Only the thread -> edge assignment changes; outputs stay in edge order.
 // One CTA sorts a chunk of kOrderChunk edges in shared memory (bitonic, 64-bit key|index).
-constexpr int kOrderChunk = 4096;
+constexpr int kOrderChunk = 2048;
 __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
   v &= 0x3ffu;
   v = (v | (v << 16)) & 0x030000ffu;
