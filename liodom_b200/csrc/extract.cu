@@ -287,6 +287,51 @@ __device__ int run_region(const RingView& rv, int lo, int hi, int epr, int* pick
   return np;
 }
 
+// Register-cached variant for regions of at most 256 items (8 per lane): keys and availability
+// live in registers, the only shared-memory traffic in the loop is the gap tests around the pick.
+// `premask`: bit b set <=> ring index lo + b is already suppressed by the previous region's picks.
+// Same selection as run_region (total order smoothness desc, index asc).
+__device__ int run_region_reg(const RingView& rv, int lo, int hi, int epr, int* picks, int ln, unsigned premask) {
+  double kk[8];
+  unsigned dead = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = lo + ln + 32 * j;
+    kk[j] = i < hi ? rv.K[i] : -1.0;
+    if (i >= hi || (i - lo < 5 && ((premask >> (i - lo)) & 1u))) dead |= 1u << j;
+  }
+  int np = 0;
+  for (;;) {
+    double bk = -1.0; int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!((dead >> j) & 1u) && kk[j] > bk) { bk = kk[j]; bi = lo + ln + 32 * j; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    if (bi == 0x7fffffff) break;            // every item already picked
+    if (bk < 0.1 || np > epr) break;        // src/feature_extractor.cc:270
+    if (ln == 0) picks[np] = bi;
+    ++np;
+    // +-5 suppression, gap-limited (src/feature_extractor.cc:280-310): lanes 0-4 forward, 8-12 backward
+    bool brk = false;
+    if (ln < 5) { const int l = ln + 1; brk = gap2(rv.P[bi + l], rv.P[bi + l - 1]) > 0.05; }
+    else if (ln >= 8 && ln < 13) { const int l = ln - 7; brk = gap2(rv.P[bi - l], rv.P[bi - l + 1]) > 0.05; }
+    const unsigned bm = __ballot_sync(0xffffffffu, brk);
+    const unsigned f = bm & 0x1fu, b = (bm >> 8) & 0x1fu;
+    const int nf = f ? (__ffs(f) - 1) : 5, nb = b ? (__ffs(b) - 1) : 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = lo + ln + 32 * j;
+      if (i >= bi - nb && i <= bi + nf) dead |= 1u << j;
+    }
+  }
+  return np;
+}
+
 __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y, ring = ring0 + blockIdx.x;   // ring0 > 0: ring-sharded extraction
@@ -368,11 +413,17 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
 
   const int total = n - 10, sector = total / R;
   const int nw = blockDim.x >> 5;
-  // speculative pass: every region on its own, marks confined to the region
+  // regions of <= 256 items of a ring held in shared memory take the register-cached path
+  const bool fast = in_smem && (sector + R) <= 256;
+  __shared__ unsigned s_spill[256];   // per region: suppression spilled into the next region (5 bits)
+  // speculative pass: every region on its own (no premask), marks confined to the region
   for (int r = w; r < R; r += nw) {
     const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
-    const int np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
+    const int np = fast ? run_region_reg(rv, lo, hi, epr, picks + r * E1, ln, 0u) : run_region(rv, lo, hi, epr, picks + r * E1, ln);
     if (ln == 0) npicks[r] = np;
+    __syncwarp();
+    const unsigned sp = region_spill(rv, picks + r * E1, np, hi, ln);
+    if (ln == 0) s_spill[r] = sp;
   }
   __syncthreads();
   // The only coupling between the regions of a ring is picked_: a pick within 5 points of the end of
@@ -384,10 +435,15 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
     for (int r = 0; r < R; ++r) {
       const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
       int np = npicks[r];
+      bool rerun = false;
       if (spill_prev) {
         bool clash = false;
         for (int k = ln; k < np; k += 32) { const int o = picks[r * E1 + k] - lo; clash |= o < 5 && ((spill_prev >> o) & 1u); }
-        if (__any_sync(0xffffffffu, clash)) {
+        rerun = __any_sync(0xffffffffu, clash);
+      }
+      if (rerun) {
+        if (fast) np = run_region_reg(rv, lo, hi, epr, picks + r * E1, ln, spill_prev);
+        else {
           // rerun with the true premask: clear the region's bits, set the spilled ones
           for (int i = (lo >> 5) + ln; i <= ((hi - 1) >> 5); i += 32) {
             unsigned m = 0xffffffffu;
@@ -399,11 +455,11 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
           if (ln < 5 && ((spill_prev >> ln) & 1u) && lo + ln < hi) bit_set(rv.bits, lo + ln);
           __syncwarp();
           np = run_region(rv, lo, hi, epr, picks + r * E1, ln);
-          if (ln == 0) npicks[r] = np;
-          __syncwarp();
         }
-      }
-      spill_prev = region_spill(rv, picks + r * E1, np, hi, ln);
+        if (ln == 0) npicks[r] = np;
+        __syncwarp();
+        spill_prev = region_spill(rv, picks + r * E1, np, hi, ln);
+      } else spill_prev = s_spill[r];
     }
   }
   __syncthreads();
