@@ -14,6 +14,7 @@ SO = os.path.join(HERE, "libliodom_b200.so")
 UNITS = {
     "extract.cu": ["-fmad=false"],
     "register.cu": ["-fmad=false"],
+    "voxelgrid.cu": ["-fmad=false"],
     "solve.cu": [],
     "map.cu": ["-fmad=false"],
     "shard.cu": [],

@@ -176,6 +176,8 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   p.slots = P.prev_frames + 1;
   p.Rcap = P.mapping ? (P.max_received_map > 0 ? P.max_received_map : 1 << 20) : 0;
   p.Mcap = p.slots * p.Ecap + p.Rcap;
+  p.Wcap = p.slots * p.Ecap;
+  p.vg_blocks = (P.filter_local_map && !P.mapping) ? (p.Wcap + kVgTile - 1) / kVgTile : 0;
   int h = 1024; while (h < p.Mcap + p.Mcap / 8) h <<= 1;   // load factor <= 0.89 even if every point had its own voxel; typically < 0.2
   p.Hcap = h;
   const size_t B = batch, L = P.scan_lines;
@@ -211,6 +213,12 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.gate, B * p.Ecap));
   CKC(dalloc(c, &d.eig, B * p.Ecap * 3));
   CKC(dalloc(c, &d.q_world, B * p.Ecap));
+  if (p.vg_blocks > 0) {   // filter_local_map: VoxelGrid of the window (voxelgrid.cu)
+    CKC(dalloc(c, &d.filtered, B * p.Wcap, false));
+    for (int k = 0; k < 2; ++k) { CKC(dalloc(c, &d.vg_key[k], B * p.Wcap, false)); CKC(dalloc(c, &d.vg_val[k], B * p.Wcap, false)); }
+    CKC(dalloc(c, &d.vg_hist, B * 256 * p.vg_blocks));
+    CKC(dalloc(c, &d.vg_heads, B * p.vg_blocks));
+  }
   { unsigned char* q = nullptr; CKC(dalloc(c, &q, B * shard_ctrl_bytes())); d.shard_ctrl = q; }
   CKC(dalloc(c, &d.shard_acc, B * 32));
   CKC(dalloc(c, &d.diag, B));

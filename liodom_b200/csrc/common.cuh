@@ -26,6 +26,7 @@ constexpr int kMaxSlots = 64;       // window slabs upper bound (prev_frames + 1
 constexpr int kRingSmemCap = 6144;  // ring points kept in shared memory by k_extract
 constexpr unsigned kGenBits = 12;   // hash generation tag width
 constexpr unsigned kCntBits = 20;
+constexpr int kVgTile = 2048;       // keys per CTA of the window-filter radix sort (256 threads x 8)
 
 // One slot of the open-addressing voxel hash: packed cell key (generation | iz | iy | ix), first
 // point of the cell's bucket in `sorted`, and (generation << kCntBits) | points in the cell.
@@ -44,6 +45,8 @@ struct DevParams {
   int slots;                         // window slabs allocated
   int chunks;                        // ceil(Ncap / kChunk)
   int batch;
+  int Wcap;                          // window capacity in points (slots * Ecap)
+  int vg_blocks;                     // ceil(Wcap / kVgTile) when filter_local_map, else 0
 };
 
 // Per-lane description of the scan being processed (rewritten every step).
@@ -69,6 +72,14 @@ struct WinState {
   // logical view of the window (oldest frame first), refreshed whenever the window changes:
   int view_prefix[kMaxSlots + 1];   // first logical index of frame k
   int view_slab[kMaxSlots];         // slab holding frame k
+  // filter_local_map (computeLocalMap, src/laser_odometry.cc:286-292): VoxelGrid(0.4) of the window
+  int vg_active;          // this build's kNN target is the filtered window
+  int vg_passes;          // 8-bit radix passes needed for the voxel index range
+  int vg_minb[3];         // floor(min * inv_leaf) per axis
+  int vg_div[3];          // voxels per axis of the bounding box
+  unsigned vg_lo[3];      // ordered-int encoded min / max of the finite window points
+  unsigned vg_hi[3];
+  unsigned vg_invalid;    // sort key of non-finite points (= number of voxels of the box)
 };
 
 // LaserOdometer state (src/laser_odometry.cc: odom_, prev_odom_, param_q, param_t, init_).
@@ -134,6 +145,11 @@ struct DevBuffers {
   uint8_t* gate;           // [B][Ecap]
   double* eig;             // [B][Ecap][3]
   float4* q_world;         // [B][Ecap]
+  float4* filtered;        // [B][Wcap] VoxelGrid(0.4) of the window (filter_local_map) or null
+  unsigned* vg_key[2];     // [B][Wcap] voxel index of each window point (radix sort ping-pong)
+  unsigned* vg_val[2];     // [B][Wcap] logical window index
+  int* vg_hist;            // [B][256 * vg_blocks] digit histograms (digit-major)
+  int* vg_heads;           // [B][vg_blocks] voxels starting in each tile
   void* shard_ctrl;        // [B] LM controller state of the point-sharded solve (solve.cu)
   double* shard_acc;       // [B][32] partial / reduced normal equations of the point-sharded solve
   FrameDiagDev* diag;      // [B]
@@ -146,6 +162,7 @@ struct LaneRange { int lane0, nlanes; };
 int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys);
 int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr);
+int launch_window_filter(const DevBuffers& d, cudaStream_t s, LaneRange lr);   // voxelgrid.cu; 0 launches when the filter is off
 int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane);
 int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr);  // + Morton ordering of the edges
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override);
@@ -185,6 +202,33 @@ __device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
   k &= 0xFFFFFFFFFFFFull;
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (unsigned)k;
+}
+
+// ---- logical window addressing -------------------------------------------------------------------
+// Frame k (oldest first) lives in slab view_slab[k] and starts at logical index view_prefix[k].  The
+// view is kept in WinState (refreshed by hash_begin, i.e. whenever the window changed) so that
+// kernels only read it.  `filt` != null: the kNN target is the VoxelGrid-filtered window instead.
+struct WinView {
+  const int* prefix;
+  const int* slab;
+  const float4* filt;
+  int nframes, total, n_received;
+};
+
+__device__ __forceinline__ void load_win_view(const DevBuffers& d, int lane_b, WinView* v, bool target = true) {
+  const WinState& ws = d.wstate[lane_b];
+  v->prefix = ws.view_prefix; v->slab = ws.view_slab;
+  v->nframes = ws.nframes; v->total = ws.view_prefix[ws.nframes];
+  v->n_received = d.p.mapping ? ws.n_received : 0;
+  v->filt = (target && d.filtered && ws.vg_active) ? d.filtered + (size_t)lane_b * d.p.Wcap : nullptr;
+}
+
+__device__ __forceinline__ float4 win_point(const DevBuffers& d, int lane_b, const WinView& v, int i) {
+  if (v.filt) return v.filt[i];
+  if (i >= v.total) return d.received[(size_t)lane_b * d.p.Rcap + (i - v.total)];
+  int lo = 0, hi = v.nframes;   // last frame with prefix <= i
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(v.prefix + mid) <= i) lo = mid; else hi = mid; }
+  return d.win[((size_t)lane_b * d.p.slots + __ldg(v.slab + lo)) * d.p.Ecap + (i - __ldg(v.prefix + lo))];
 }
 
 }  // namespace liodom

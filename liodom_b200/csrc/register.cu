@@ -12,29 +12,6 @@ namespace liodom {
 // ---------------------------------------------------------------------------------------
 // window addressing
 // ---------------------------------------------------------------------------------------
-// Logical window addressing: frame k (oldest first) lives in slab view_slab[k] and starts at logical
-// index view_prefix[k].  The view is kept in WinState (refreshed by hash_begin, i.e. whenever the
-// window changed) so that kernels only read it.
-struct WinView {
-  const int* prefix;
-  const int* slab;
-  int nframes, total, n_received;
-};
-
-__device__ __forceinline__ void load_win_view(const DevBuffers& d, int lane_b, WinView* v) {
-  const WinState& ws = d.wstate[lane_b];
-  v->prefix = ws.view_prefix; v->slab = ws.view_slab;
-  v->nframes = ws.nframes; v->total = ws.view_prefix[ws.nframes];
-  v->n_received = d.p.mapping ? ws.n_received : 0;
-}
-
-__device__ __forceinline__ float4 win_point(const DevBuffers& d, int lane_b, const WinView& v, int i) {
-  if (i >= v.total) return d.received[(size_t)lane_b * d.p.Rcap + (i - v.total)];
-  int lo = 0, hi = v.nframes;   // last frame with prefix <= i
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(v.prefix + mid) <= i) lo = mid; else hi = mid; }
-  return d.win[((size_t)lane_b * d.p.slots + __ldg(v.slab + lo)) * d.p.Ecap + (i - __ldg(v.prefix + lo))];
-}
-
 // Called by exactly one thread after the window changed: start a new hash generation.
 __device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
   WinState& ws = d.wstate[lane_b];
@@ -47,6 +24,10 @@ __device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
   ws.gen = ws.gen + 1u;
   ws.bump = 0;
   ws.hash_points = ws.total + (d.p.mapping ? ws.n_received : 0);
+  // computeLocalMap (src/laser_odometry.cc:286): filter iff the window is full and mapping is off;
+  // launch_window_filter then replaces the target (and hash_points) before the hash is built.
+  ws.vg_active = (d.filtered && d.p.filter_local_map && !d.p.mapping && ws.nframes == d.p.prev_frames) ? 1 : 0;
+  for (int k = 0; k < 3; ++k) { ws.vg_lo[k] = 0xffffffffu; ws.vg_hi[k] = 0u; }
 }
 
 // LocalMapManager::addPointCloud bookkeeping (src/laser_odometry.cc:34-60): the new frame
@@ -134,10 +115,11 @@ int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   int blocks = (d.p.Mcap + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   const dim3 g(blocks, nlanes);
+  const int nf = launch_window_filter(d, s, lr);
   k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
   k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
   k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
-  return 3;
+  return 3 + nf;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -656,7 +638,7 @@ int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane) {
 // gather the window in logical order (LocalMapManager::getLocalMap)
 __global__ void __launch_bounds__(256) k_lmap_gather(DevBuffers d, int lane_b, float4* out) {
   WinView v;
-  load_win_view(d, lane_b, &v);
+  load_win_view(d, lane_b, &v, false);   // LocalMapManager::getLocalMap returns the unfiltered window
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.total; i += gridDim.x * blockDim.x) out[i] = win_point(d, lane_b, v, i);
 }
 int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out) {

@@ -303,3 +303,89 @@ def test_batched_lanes_match_single_lane(cuda_lib):
         for k in range(3):
             assert np.array_equal(poses[k], single[k][f]), (f, k)
     ctx.close()
+
+
+# ---- filter_local_map: VoxelGrid(0.4) of the full window as the kNN target (src/laser_odometry.cc:286-292)
+def _check_assoc(g, o, min_sel):
+    ok = o["tie"] == 0
+    assert np.array_equal(g["gate"][ok], o["gate"][ok])
+    sel = ok & ((o["gate"] & 1) == 1)
+    assert sel.sum() >= min_sel
+    assert np.array_equal(g["knn_idx"][sel], o["knn_idx"][sel])
+    assert np.array_equal(g["knn_d2"][sel].view(np.uint32), o["knn_d2"][sel].view(np.uint32))
+    assert np.array_equal(g["eig"][sel].view(np.uint64), o["eig"][sel].view(np.uint64))
+
+
+def test_window_filter_teacher_forced(cuda_lib):
+    """The filter applies only once the window holds prev_frames frames; then the kNN target is
+    pcl::VoxelGrid(0.4) of the window: same centroids (bit patterns), same order, same 5-NN."""
+    K = 6
+    scans, gt = get_sequence("hdl64", 1000, K + 3)
+    op = oracle.make_params(prev_frames=K, filter_local_map=1)
+    edges_seq = _edges_of(op, scans)
+    ctx = api.Context(prev_frames=K, filter_local_map=1, max_points=131072)
+    frames = []
+    for f in range(K + 2):
+        w = oracle.transform(edges_seq[f], np.linalg.inv(gt[0]) @ gt[f])
+        ctx.lmap_add(w)
+        frames = (frames + [w])[-K:]
+        window = np.concatenate(frames)
+        target = oracle.voxelgrid(window, 0.4) if len(frames) == K else window
+        if len(frames) == K:
+            assert 0 < len(target) < len(window)
+        T = np.linalg.inv(gt[0]) @ gt[f + 1]
+        T = T.copy()
+        T[:3, 3] += [0.04, -0.02, 0.01]
+        o = oracle.associate(edges_seq[f + 1], T, target, knn_method=0)
+        g = ctx.associate(edges_seq[f + 1], T)
+        assert g["n_map"] == len(target), (f, g["n_map"], len(target), len(window))
+        _check_assoc(g, o, 100)
+        # LocalMapManager::getLocalMap keeps returning the unfiltered window
+        lw, nf = ctx.lmap_get()
+        assert nf == len(frames) and np.array_equal(lw.view(np.uint32), window.view(np.uint32))
+    ctx.close()
+
+
+def test_window_filter_random_clouds(cuda_lib):
+    """Dense random clouds (many points per voxel, negative coordinates, non-finite points, an empty
+    frame): voxel order and the input-order float centroids must match the restated VoxelGrid."""
+    rng = np.random.default_rng(11)
+    K = 3
+    ctx = api.Context(prev_frames=K, filter_local_map=1, scan_lines=16, scan_regions=8, edges_per_region=40, max_points=4096)
+    frames = []
+    for f in range(7):
+        n = [5000, 0, 3000, 5248, 17, 4000, 2500][f]
+        w = (rng.normal(size=(n, 4)) * [3.0, 2.0, 0.7, 1.0]).astype(np.float32)
+        if f == 3:
+            w[::97, 2] = np.nan
+            w[5::211, 0] = np.inf
+        ctx.lmap_add(w)
+        frames = (frames + [w])[-K:]
+        window = np.concatenate(frames)
+        target = oracle.voxelgrid(window, 0.4) if len(frames) == K else window
+        q = (rng.normal(size=(600, 4)) * [2.0, 1.5, 0.5, 1.0]).astype(np.float32)
+        o = oracle.associate(q, np.eye(4), target, knn_method=0)
+        g = ctx.associate(q, np.eye(4))
+        assert g["n_map"] == len(target), (f, g["n_map"], len(target))
+        _check_assoc(g, o, 50)
+    ctx.close()
+
+
+def test_register_teacher_forced_window_filter(cuda_lib):
+    kw = dict(prev_frames=5, filter_local_map=1)
+    _run_teacher_forced("hdl64", 1002, 10, kw, kw, 131072)
+
+
+def test_batched_window_filter_free_running(cuda_lib):
+    """filter_local_map through the batched whole path: lanes at different window fill levels."""
+    seqs = [get_sequence("hdl64_small", 1000 + k, 8)[0] for k in range(2)]
+    op = oracle.make_params(prev_frames=4, filter_local_map=1)
+    refs = [oracle.run_sequence(op, sq)[0] for sq in seqs]
+    ctx = api.Context(prev_frames=4, filter_local_map=1, max_points=32768, batch=2)
+    for f in range(8):
+        ctx.scan_batch([seqs[0][f], seqs[1][f]])
+        poses, _ = ctx.results()
+        for k in range(2):
+            dt, dr = pose_err(poses[k], refs[k][f])
+            assert dt < 1e-3 and dr < 1e-4, (f, k, dt, dr)
+    ctx.close()
