@@ -21,7 +21,7 @@ UNITS = {
     "cabi.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "g++"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "g++"] + os.environ.get("LIODOM_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):

@@ -180,6 +180,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   p.vg_blocks = (P.filter_local_map && !P.mapping) ? (p.Wcap + kVgTile - 1) / kVgTile : 0;
   int h = 1024; while (h < p.Mcap + p.Mcap / 8) h <<= 1;   // load factor <= 0.89 even if every point had its own voxel; typically < 0.2
   p.Hcap = h;
+  p.Bwords = h / 2;   // 16 filter bits per hash slot: a few % false positives (each costs one extra probe, never a wrong answer)
   const size_t B = batch, L = P.scan_lines;
   CKC(dalloc(c, &d.scan, B));
   CKC(dalloc(c, &d.ring_id, B * p.Ncap, false));
@@ -204,6 +205,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.sorted, B * p.Mcap));
   CKC(dalloc(c, &d.lin, B * p.Mcap));
   CKC(dalloc(c, &d.htab, B * p.Hcap));
+  CKC(dalloc(c, &d.bloom, B * p.Bwords));
   CKC(dalloc(c, &d.pt_slot, B * p.Mcap));
   CKC(dalloc(c, &d.pt_rank, B * p.Mcap));
   CKC(dalloc(c, &d.perm, B * p.Ecap));

@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
       }
       slot = (slot + 1) & mask;
     }
+    if (owner) {   // first point of the cell: publish it in the occupancy filter read by k_associate
+      const int ix = cell_of(pt.x);
+      atomicOr(d.bloom + (size_t)lane_b * d.p.Bwords + bloom_word_index(ix >> 5, cell_of(pt.y), cell_of(pt.z), (unsigned)d.p.Bwords - 1u), 1u << (ix & 31));
+    }
     atomicMax(&tab[slot].cnt, gen << kCntBits);
     const unsigned rank = atomicAdd(&tab[slot].cnt, 1u) & ((1u << kCntBits) - 1u);
     *pslot = slot | (owner ? 0x80000000u : 0u);
@@ -116,6 +120,7 @@ int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   if (blocks > 148 * 4) blocks = 148 * 4;
   const dim3 g(blocks, nlanes);
   const int nf = launch_window_filter(d, s, lr);
+  cudaMemsetAsync(d.bloom + (size_t)lane0 * d.p.Bwords, 0, sizeof(unsigned) * (size_t)d.p.Bwords * nlanes, s);
   k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
   k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
   k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
@@ -181,7 +186,7 @@ __global__ void k_predict(DevBuffers d, int lane0) {
   dg.pred_pose[12] = dg.pred_pose[13] = dg.pred_pose[14] = 0.0; dg.pred_pose[15] = 1.0;
 }
 
-// Morton ordering of the edges by the 0.5 m cell of their predicted world position: threads of
+// Morton ordering of the edges by the kCell-sized cell of their predicted world position: threads of
 // one k_associate warp then walk the same / neighbouring hash buckets (broadcast loads, similar
 // trip counts).  Only the thread -> edge assignment changes; outputs stay in edge order.
 // One CTA sorts a chunk of kOrderChunk edges in shared memory (bitonic, 64-bit key|index).
@@ -304,24 +309,32 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
 
 // Exact 5-NN of one query, one thread per edge, over the kCell = 0.5 m voxel hash.
 //
-// Exactness.  Every map point with float d2 < (0.5 R)^2 lies inside the (2R+1)^3 cell cube
-// around the query's cell: an outside point differs by >= 0.5 R on some axis, and float
-// subtraction, squaring and summation are monotone.  So after the 27-cell cube the list is
-// final iff its 5th entry has d2 < 0.25; otherwise the 98 cells of the next shell are added,
-// which is exact for the reference's gate d2[4] < 1.0 (src/laser_odometry.cc:324).
+// Exactness.  Every map point with float d2 < (kCell R)^2 lies inside the (2R+1)^3 cell cube
+// around the query's cell: an outside point differs by >= kCell R on some axis, and float
+// subtraction, squaring and summation are monotone.  So after the 27-cell cube (R = 1) the list is
+// final iff its 5th entry has d2 < kCell^2 = 0.25 (92 % of the C1 edges); the others go through
+// the fallback stage, which visits every cell of the 5^3 cube (R = 2, radius 1 m) that can still
+// hold a candidate — exact for the reference's gate d2[4] < 1.0 (src/laser_odometry.cc:324).
 // Pruning.  cell_min_d2 evaluates L2_Simple on the per-axis gaps to the cell box with the same
 // float operations as the point distance, hence it is <= the float d2 of every point of the
 // cell; a cell is skipped only when that bound is >= 1.0 or strictly above the current 5th
-// best, so no candidate (nor a tie on d2, which is broken by the lower logical index) is lost.
+// best, so no candidate (nor a tie on d2, which is broken by the lower logical index) is lost.  A
+// whole x-row of cells is skipped on its (y, z) gaps alone: fl(gy^2 + gz^2) <= the bound of each
+// of its cells, again by monotonicity.
+// Empty cells cost no hash probe: an occupancy filter (one bit per cell, 32 x-consecutive cells per
+// word, word = hash(ix >> 5, iy, iz)) is read one row at a time; a false positive costs one probe.
 // Sorted 5-list of packed candidates (float bits of d2) << 32 | logical index: d2 >= 0, so the
 // unsigned 64-bit order is the (d2, index) order.  Empty entries are ~0.
 struct Knn5 {
   unsigned long long k[5];
 };
 constexpr unsigned long long kEmptyCand = ~0ull;
+constexpr float kProvenD2 = kCell * kCell;   // 5th-best below this: the 27-cell cube was enough
+constexpr int kFbRadius = (int)(1.0f / kCell);   // cells covering the 1 m gate radius
+constexpr int kFbSide = 2 * kFbRadius + 1;
 
 __device__ __forceinline__ float axis_gap(float q, int cell) {
-  const float lo = 0.5f * (float)cell, hi = lo + 0.5f;   // exact
+  const float lo = kCell * (float)cell, hi = lo + kCell;   // exact
   return q < lo ? __fsub_rn(lo, q) : (q > hi ? __fsub_rn(q, hi) : 0.0f);
 }
 
@@ -353,20 +366,22 @@ __device__ __forceinline__ uint2 hash_lookup(const HashEntry* __restrict__ tab, 
   }
 }
 
+// Occupancy bits of the n <= 32 cells ix0 .. ix0 + n - 1 of row (iy, iz); bit b = cell ix0 + b.
+__device__ __forceinline__ unsigned bloom_row(const unsigned* __restrict__ bloom, unsigned bmask, int ix0, int n, int iy, int iz) {
+  const int w0 = ix0 >> 5, w1 = (ix0 + n - 1) >> 5;
+  const unsigned a = __ldg(bloom + bloom_word_index(w0, iy, iz, bmask));
+  const unsigned b = w1 != w0 ? __ldg(bloom + bloom_word_index(w1, iy, iz, bmask)) : 0u;
+  return __funnelshift_r(a, b, ix0 & 31) & ((1u << n) - 1u);
+}
+
+__device__ __forceinline__ float sq_sum2(float gy, float gz) { return __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)); }
+
 __device__ __forceinline__ float cell_min_d2(float qx, float qy, float qz, int ix, int iy, int iz) {
   const float gx = axis_gap(qx, ix), gy = axis_gap(qy, iy), gz = axis_gap(qz, iz);
   return __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
 }
 
-// `ub`: a known upper bound on the final 5th-best d2 (3e38 when none): larger d2 cannot enter.
-__device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab, const float4* __restrict__ sorted,
-                                              unsigned hmask, unsigned gen, int ix, int iy, int iz,
-                                              float qx, float qy, float qz, float ub, Knn5& k) {
-  const float dmin = cell_min_d2(qx, qy, qz, ix, iy, iz);
-  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
-  const uint2 sc = hash_lookup(tab, hmask, gen, ix, iy, iz);
-  const unsigned cn = sc.y;
-  const float4* b = sorted + sc.x;
+__device__ __forceinline__ void knn_scan_bucket(const float4* __restrict__ b, unsigned cn, float qx, float qy, float qz, float ub, Knn5& k) {
   unsigned j = 0;
   for (; j + 4 <= cn; j += 4) {   // four independent loads in flight
     const float4 p0 = __ldg(b + j), p1 = __ldg(b + j + 1), p2 = __ldg(b + j + 2), p3 = __ldg(b + j + 3);
@@ -376,13 +391,38 @@ __device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab,
   for (; j < cn; ++j) knn_offer(__ldg(b + j), qx, qy, qz, ub, k);
 }
 
+// `ub`: a known upper bound on the final 5th-best d2 (3e38 when none): larger d2 cannot enter.
+__device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab, const float4* __restrict__ sorted,
+                                              unsigned hmask, unsigned gen, int ix, int iy, int iz,
+                                              float qx, float qy, float qz, float ub, Knn5& k) {
+  const float dmin = cell_min_d2(qx, qy, qz, ix, iy, iz);
+  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
+  const uint2 sc = hash_lookup(tab, hmask, gen, ix, iy, iz);
+  knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, ub, k);
+}
+
+// The occupied cells ix0 + b (b < n) of row (iy, iz), except those in `skip`, pruned and scanned.
+__device__ __forceinline__ void knn_scan_row(const HashEntry* __restrict__ tab, const float4* __restrict__ sorted,
+                                             const unsigned* __restrict__ bloom, unsigned hmask, unsigned bmask, unsigned gen,
+                                             int ix0, int n, unsigned skip, int iy, int iz,
+                                             float qx, float qy, float qz, float ub, Knn5& k) {
+  const float g2 = sq_sum2(axis_gap(qy, iy), axis_gap(qz, iz));
+  if (g2 >= 1.0f || __float_as_uint(g2) > (unsigned)(k.k[4] >> 32) || g2 > ub) return;
+  unsigned mask = bloom_row(bloom, bmask, ix0, n, iy, iz) & ~skip;
+  while (mask) {
+    const int bsel = __ffs(mask) - 1;
+    mask &= mask - 1;
+    knn_scan_cell(tab, sorted, hmask, gen, ix0 + bsel, iy, iz, qx, qy, qz, ub, k);
+  }
+}
+
 constexpr int kAssocThreads = 64;
 
 // G threads per edge (G = 1 for large batches: least work; G = 4 when few edges are in flight:
 // shorter critical path): transform (A.1: double math, float store), exact 5-NN, line gate
 // (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
 template <int G>
-__global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(DevBuffers d, int lane0, int outer_it, int force,
+__global__ void __launch_bounds__(kAssocThreads, G == 1 ? 20 : 8) k_associate(DevBuffers d, int lane0, int outer_it, int force,
                                                                               const double* pose_override, int shard_rank, int shard_world) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y;
@@ -396,7 +436,7 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(De
   const int gl = ln & (G - 1);                                   // lane inside the edge's group
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
   bool match = false;
-  if (active && (t - ln / G) < E) {   // warp-uniform: the shell search below is cooperative
+  if (active && (t - ln / G) < E) {   // warp-uniform: the fallback search below is cooperative
     const WinState& ws = d.wstate[lane_b];
     const double* T = pose_override ? pose_override : os.odom;
     const bool mine = t < E;
@@ -405,28 +445,28 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(De
     const float4 c = mine ? d.edges[(size_t)lane_b * p.Ecap + e] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
     const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
-    const unsigned hmask = (unsigned)p.Hcap - 1u;
+    const unsigned hmask = (unsigned)p.Hcap - 1u, bmask = (unsigned)p.Bwords - 1u;
     const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
     const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
+    const unsigned* bloom = d.bloom + (size_t)lane_b * p.Bwords;
     Knn5 k;
 #pragma unroll
     for (int r = 0; r < 5; ++r) k.k[r] = kEmptyCand;
     const bool searchable = mine && ws.hash_points > 0 && isfinite(qx) && isfinite(qy) && isfinite(qz);
     const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
-    // ---- level 1: the 27-cell cube of every edge, own cell first (it sets the pruning bound).
-    // (A cell-major variant — the warp walking the union of its cubes with broadcast loads — was
-    // measured slower: Morton-adjacent edges still need mostly different cells after pruning.)
+    // ---- level 1: the 27-cell cube, own cell first (it sets the pruning bound), then its 9 x-rows.
+    // (A cell-major variant — the warp walking the union of its cubes with broadcast loads — and a
+    // warp-per-edge variant with the buckets concatenated across the lanes were measured slower.)
     if (G == 1) {
       if (searchable) {
-        knn_scan_cell(tab, sorted, hmask, gen, cx, cy, cz, qx, qy, qz, 3.0e38f, k);
-        for (int ci = 0; ci < 27; ++ci) {
-          const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
-          if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
-        }
+        const uint2 sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
+        knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, 3.0e38f, k);
+        for (int r = 0; r < 9; ++r)
+          knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, cx - 1, 3, r == 4 ? 2u : 0u, cy + r % 3 - 1, cz + r / 3 - 1, qx, qy, qz, 3.0e38f, k);
       }
     } else {
       // the group strides over the own cell together, shares the tightest 5th-best as a bound, splits
-      // the 26 neighbours round-robin and merges the G sorted lists by 5 rounds of group arg-min
+      // the 9 rows round-robin and merges the G sorted lists by 5 rounds of group arg-min
       if (searchable) {
         const uint2 sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
         for (unsigned j = gl; j < sc.y; j += G) knn_offer(__ldg(sorted + sc.x + j), qx, qy, qz, 3.0e38f, k);
@@ -434,10 +474,8 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(De
       const unsigned ubb = __reduce_min_sync(gmask, (unsigned)(k.k[4] >> 32));
       const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
       if (searchable)
-        for (int ci = gl; ci < 27; ci += G) {
-          const int dz = ci / 9 - 1, dy = (ci / 3) % 3 - 1, dx = ci % 3 - 1;
-          if (ci != 13) knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, ub, k);
-        }
+        for (int r = gl; r < 9; r += G)
+          knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, cx - 1, 3, r == 4 ? 2u : 0u, cy + r % 3 - 1, cz + r / 3 - 1, qx, qy, qz, ub, k);
       __syncwarp(gmask);
       unsigned long long res[5];
 #pragma unroll
@@ -456,10 +494,11 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(De
 #pragma unroll
       for (int r = 0; r < 5; ++r) k.k[r] = res[r];   // the merged list, uniform over the group
     }
-    // Edges whose 5th neighbour is not proven inside the 0.5 m radius: the whole warp scans the
-    // 98 cells of the next shell (lane l takes cells l, l+32, ...), bounded by the owner's
-    // current 5th best, then the per-lane lists are merged by 5 rounds of warp arg-min.
-    unsigned need = __ballot_sync(0xffffffffu, searchable && gl == 0 && (unsigned)(k.k[4] >> 32) >= __float_as_uint(0.25f));
+    // ---- fallback: edges whose 5th neighbour is not proven inside the kCell radius.  The whole warp
+    // walks the 25 x-rows of the owner's 5^3 cube (one row per lane; rows and cells
+    // beyond the owner's current 5th best or the 1 m gate are skipped on their bounds, the 27 cells of
+    // level 1 are masked out), then the per-lane lists are merged by 5 rounds of warp arg-min.
+    unsigned need = __ballot_sync(0xffffffffu, searchable && gl == 0 && (unsigned)(k.k[4] >> 32) >= __float_as_uint(kProvenD2));
     while (need) {
       const int owner = __ffs(need) - 1;
       need &= need - 1;
@@ -473,10 +512,10 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 16 : 8) k_associate(De
         const unsigned long long v = __shfl_sync(0xffffffffu, k.k[r], owner);
         l.k[r] = ln == 0 ? v : kEmptyCand;
       }
-      for (int ci = ln; ci < 125; ci += 32) {
-        const int dz = ci / 25 - 2, dy = (ci / 5) % 5 - 2, dx = ci % 5 - 2;
-        if (abs(dx) == 2 || abs(dy) == 2 || abs(dz) == 2)
-          knn_scan_cell(tab, sorted, hmask, gen, jcx + dx, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
+      for (int rr = ln; rr < kFbSide * kFbSide; rr += 32) {
+        const int dy = rr % kFbSide - kFbRadius, dz = rr / kFbSide - kFbRadius;
+        const unsigned inner = (abs(dy) <= 1 && abs(dz) <= 1) ? (7u << (kFbRadius - 1)) : 0u;
+        knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, jcx - kFbRadius, kFbSide, inner, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
       }
       __syncwarp();
 #pragma unroll
