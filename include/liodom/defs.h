@@ -58,15 +58,38 @@ struct alignas(16) Point {
 };
 static_assert(sizeof(Point) == 32, "liodom::Point must match pcl::PointXYZI");
 
+/* sensor_msgs/PointField + PointCloud2: what lidarClb / mapClb receive (src/liodom_node.cc:40-64). */
+struct PointField {
+  enum { INT8 = 1, UINT8, INT16, UINT16, INT32, UINT32, FLOAT32, FLOAT64 };
+  std::string name;
+  uint32_t offset = 0;
+  uint8_t datatype = 0;
+  uint32_t count = 1;
+};
+struct PointCloud2 {
+  typedef std::shared_ptr<PointCloud2> Ptr;
+  typedef std::shared_ptr<const PointCloud2> ConstPtr;
+  Header header;
+  uint32_t height = 0, width = 0;
+  std::vector<PointField> fields;
+  bool is_bigendian = false;
+  uint32_t point_step = 0, row_step = 0;
+  std::vector<uint8_t> data;
+  bool is_dense = true;
+};
+
 struct PointCloud {     // the part of pcl::PointCloud<PointXYZI> the reference uses
   typedef std::shared_ptr<PointCloud> Ptr;
   typedef std::shared_ptr<const PointCloud> ConstPtr;
   std::vector<Point> points;
+  /* Set by fromROSMsgDeferred: the message bytes travel to the device as they are and the split
+   * kernel reads the fields in place; `points` then stays empty until someone asks for them. */
+  PointCloud2::ConstPtr raw;
   uint32_t width = 0, height = 0;
   bool is_dense = true;
   Header header;
-  size_t size() const { return points.size(); }
-  bool empty() const { return points.empty(); }
+  size_t size() const { return raw ? (size_t)raw->width * raw->height : points.size(); }
+  bool empty() const { return size() == 0; }
   void clear() { points.clear(); width = height = 0; }
   void push_back(const Point& p) { points.push_back(p); width = (uint32_t)points.size(); height = 1; }
   const Point& at(int column, int row) const { return points[(size_t)row * width + column]; }

@@ -13,8 +13,18 @@
 #include <liodom/stats.h>
 
 struct liodom_ctx;
+struct liodom_cloud_layout;
 
 namespace liodom {
+
+/* pcl::fromROSMsg's field matching (pcl/conversions.h createMapping: same name, datatype FLOAT32,
+ * count 1) for liodom::Point = PointXYZI.  False when x, y or z has no match or the message is
+ * big-endian; a missing intensity gives off_intensity = -1 (the field stays 0, PCL only warns). */
+bool cloudLayoutFromFields(const PointCloud2& msg, liodom_cloud_layout* layout);
+/* Host-side pcl::fromROSMsg (used for the small received local map, mapClb src/liodom_node.cc:57-64). */
+bool fromROSMsg(const PointCloud2& msg, PointCloud& cloud);
+/* lidarClb's conversion (src/liodom_node.cc:40-44) without touching the points: keeps the message. */
+bool fromROSMsgDeferred(const PointCloud2::ConstPtr& msg, PointCloud& cloud);
 
 class FeatureExtractor {
  public:

@@ -82,6 +82,25 @@ int liodom_extract(liodom_ctx* ctx, int lane, const void* pts, int n, int stride
                    int width, int height, float* edges_xyzi, int* n_edges,
                    int32_t* edge_ring, int32_t* edge_idx, double* keys);
 
+/* Where the four FLOAT32 fields of liodom::Point sit inside one point of a sensor_msgs/PointCloud2
+ * `data` blob.  Replaces pcl::fromROSMsg in lidarClb / mapClb (src/liodom_node.cc:43-44, :62-63): the
+ * message bytes go to the device as they are and the kernels read the fields in place.  The facade's
+ * liodom::cloudLayoutFromFields derives it from the message's field list by PCL's rules (match by
+ * name, datatype FLOAT32, count 1; a missing intensity stays 0).  point_step need not be a multiple
+ * of 4 (the 22-byte velodyne PointXYZIRT works).  Big-endian messages are refused: PCL copies bytes
+ * verbatim and would misread them. */
+typedef struct liodom_cloud_layout {
+  int point_step;     /* PointCloud2.point_step */
+  int row_step;       /* PointCloud2.row_step; 0 = width * point_step */
+  int off_x, off_y, off_z;
+  int off_intensity;  /* < 0: the message has no FLOAT32 "intensity" field */
+  int is_bigendian;
+} liodom_cloud_layout;
+
+/* liodom_extract on a raw PointCloud2 blob (parity tests of the decode path). */
+int liodom_extract_layout(liodom_ctx* ctx, int lane, const void* data, int n, const liodom_cloud_layout* layout,
+                          int width, int height, float* edges_xyzi, int* n_edges, int32_t* edge_ring, int32_t* edge_idx);
+
 /* ---- LocalMapManager (src/laser_odometry.cc:24-69) -------------------------------- */
 int liodom_lmap_add(liodom_ctx* ctx, int lane, const float* xyzi, int n);
 int liodom_lmap_get(liodom_ctx* ctx, int lane, float* xyzi, int cap, int* n_points, int* n_frames);
@@ -146,6 +165,9 @@ int liodom_register(liodom_ctx* ctx, int lane, const float* edges_xyzi, int n_ed
  * (which synchronises).  Steps may be pipelined: up to 2 scans in flight. */
 int liodom_scan_batch(liodom_ctx* ctx, const void* const* pts, const int* n, int stride_bytes,
                       int width, int height, int on_device);
+/* Same with raw PointCloud2 blobs: data[l] holds height x row_step bytes (n[l] = width * height points). */
+int liodom_scan_batch_layout(liodom_ctx* ctx, const void* const* data, const int* n, const liodom_cloud_layout* layout,
+                             int width, int height, int on_device);
 /* poses16_out[batch*16], n_edges_out[batch] (either may be NULL) of the last enqueued scan. */
 int liodom_scan_results(liodom_ctx* ctx, double* poses16_out, int* n_edges_out);
 /* Same for age 0 (last enqueued) or 1 (the scan before it): with two scans in flight the caller

@@ -21,6 +21,12 @@ class Params(ctypes.Structure):
                 ("max_points", ctypes.c_int), ("max_received_map", ctypes.c_int)]
 
 
+class CloudLayout(ctypes.Structure):
+    """liodom_cloud_layout: where x, y, z, intensity (FLOAT32) sit in a sensor_msgs/PointCloud2 point."""
+    _fields_ = [("point_step", ctypes.c_int), ("row_step", ctypes.c_int), ("off_x", ctypes.c_int), ("off_y", ctypes.c_int),
+                ("off_z", ctypes.c_int), ("off_intensity", ctypes.c_int), ("is_bigendian", ctypes.c_int)]
+
+
 class SolveSummary(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int), ("successful_steps", ctypes.c_int), ("termination", ctypes.c_int),
                 ("num_residual_blocks", ctypes.c_int), ("cost_evals", ctypes.c_int), ("jac_evals", ctypes.c_int),
@@ -158,6 +164,27 @@ class Context:
         if not debug:
             return edges[:e].copy()
         return dict(edges=edges[:e].copy(), ring=er[:e].copy(), idx=ei[:e].copy(), keys=keys)
+
+    def extract_layout(self, data, n, layout, lane=0, width=0, height=0):
+        """liodom_extract on a raw PointCloud2 blob (uint8 array); -> dict(edges, ring, idx)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        edges = np.empty((self.max_edges, 4), np.float32)
+        er = np.empty(self.max_edges, np.int32)
+        ei = np.empty(self.max_edges, np.int32)
+        ne = ctypes.c_int()
+        self._ck(self.lib.liodom_extract_layout(self.h, lane, _p(data), n, ctypes.byref(layout), width, height, _p(edges),
+                                                ctypes.byref(ne), _p(er), _p(ei)))
+        e = ne.value
+        return dict(edges=edges[:e].copy(), ring=er[:e].copy(), idx=ei[:e].copy())
+
+    def scan_batch_layout(self, blobs, counts, layout, width=0, height=0):
+        """blobs: list of `batch` uint8 host arrays holding raw PointCloud2 data."""
+        assert len(blobs) == self.batch
+        arrs = [np.ascontiguousarray(b, dtype=np.uint8) for b in blobs]
+        ptrs = (_vp * self.batch)(*[a.ctypes.data for a in arrs])
+        ns = (ctypes.c_int * self.batch)(*counts)
+        self._keep = arrs
+        self._ck(self.lib.liodom_scan_batch_layout(self.h, ptrs, ns, ctypes.byref(layout), width, height, 0))
 
     # ---- LocalMapManager -----------------------------------------------------------------
     def lmap_add(self, pts, lane=0):

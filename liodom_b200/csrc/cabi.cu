@@ -4,6 +4,7 @@
 #include "../../include/liodom_b200.h"
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -290,19 +291,67 @@ static int check_lane(liodom_ctx* c, int lane) {
   return 0;
 }
 
-// Copy one host scan to the device staging area of `lane` (buffer 0) and publish its descriptor.
-static int stage_scan(liodom_ctx* c, int lane, const void* pts, int n, int stride_bytes, int width, int height) {
-  if (n < 0 || stride_bytes < 12 || (stride_bytes & 3)) return fail(c, LIODOM_E_INVALID, "bad n/stride_bytes (%d, %d)", n, stride_bytes);
-  if (n > c->d.p.Ncap) return fail(c, LIODOM_E_CAPACITY, "scan of %d points exceeds max_points capacity %d", n, c->d.p.Ncap);
+// Where the four FLOAT32 fields of a point live (liodom_cloud_layout, or the fixed stride-only form).
+struct Layout {
+  int step = 16, row_step = 0, ox = 0, oy = 4, oz = 8, oi = 12, generic = 0;
+};
+
+static int layout_from_stride(liodom_ctx* c, int stride_bytes, Layout* L) {
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(c, LIODOM_E_INVALID, "bad stride_bytes %d", stride_bytes);
+  *L = Layout{};
+  L->step = stride_bytes;
+  return 0;
+}
+
+// pcl::fromROSMsg (src/liodom_node.cc:43-44) copies each matched field byte for byte; it does not
+// convert endianness, so big-endian messages are refused instead of decoded wrongly.
+static int layout_from_user(liodom_ctx* c, const liodom_cloud_layout* u, int width, Layout* L) {
+  if (!u) return fail(c, LIODOM_E_INVALID, "layout is NULL");
+  if (u->is_bigendian) return fail(c, LIODOM_E_INVALID, "big-endian clouds are not supported (pcl::fromROSMsg copies bytes verbatim)");
+  if (u->point_step < 12) return fail(c, LIODOM_E_INVALID, "point_step %d too small for x,y,z", u->point_step);
+  const int offs[4] = {u->off_x, u->off_y, u->off_z, u->off_intensity};
+  for (int k = 0; k < 4; ++k) {
+    if (k == 3 && offs[k] < 0) continue;   // no intensity field: left 0
+    if (offs[k] < 0 || offs[k] + 4 > u->point_step) return fail(c, LIODOM_E_INVALID, "field offset %d outside the %d-byte point", offs[k], u->point_step);
+  }
+  const long long packed_row = (long long)(width > 0 ? width : 0) * u->point_step;
+  if (u->row_step != 0 && u->row_step < packed_row) return fail(c, LIODOM_E_INVALID, "row_step %d smaller than width * point_step", u->row_step);
+  L->step = u->point_step;
+  L->row_step = (u->row_step != 0 && u->row_step != packed_row) ? u->row_step : 0;
+  L->ox = u->off_x; L->oy = u->off_y; L->oz = u->off_z; L->oi = u->off_intensity < 0 ? -1 : u->off_intensity;
+  L->generic = 1;
+  return 0;
+}
+
+static size_t scan_bytes(const Layout& L, int n, int width, int height) {
+  if (L.generic && L.row_step && width > 0) return (size_t)(height > 0 ? height : (n + width - 1) / width) * L.row_step;
+  return (size_t)n * L.step;
+}
+
+static void fill_desc(ScanDesc* sd, const void* pts, int n, const Layout& L, int width, int height) {
+  sd->pts = pts; sd->n = n; sd->stride_bytes = L.step; sd->width = width > 0 ? width : 1; sd->height = height;
+  sd->generic = L.generic; sd->row_step = L.row_step; sd->off_x = L.ox; sd->off_y = L.oy; sd->off_z = L.oz; sd->off_i = L.oi;
+}
+
+static int check_scan_shape(liodom_ctx* c, int lane, int n, const Layout& L, int width, int height) {
+  if (n < 0 || n > c->d.p.Ncap) return fail(c, LIODOM_E_CAPACITY, "lane %d: %d points exceed max_points capacity %d", lane, n, c->d.p.Ncap);
   if (c->params.lidar_type == 1) {
-    if (width <= 0 || height <= 0 || (long long)width * height != n) return fail(c, LIODOM_E_INVALID, "organised cloud needs width*height == n");
+    if (width <= 0 || height <= 0 || (long long)width * height != n) return fail(c, LIODOM_E_INVALID, "lane %d: organised cloud needs width*height == n", lane);
     if (height > c->params.scan_lines) return fail(c, LIODOM_E_INVALID, "cloud height %d exceeds scan_lines %d (the reference overruns its scans vector here)", height, c->params.scan_lines);
   }
-  int rc = ensure_dev_in(c, (size_t)c->d.p.Ncap * 32);
+  if (L.row_step && (width <= 0 || n % width != 0)) return fail(c, LIODOM_E_INVALID, "lane %d: padded rows need n to be a multiple of width", lane);
+  return 0;
+}
+
+// Copy one host scan to the device staging area of `lane` (buffer 0) and publish its descriptor.
+static int stage_scan(liodom_ctx* c, int lane, const void* pts, int n, const Layout& L, int width, int height) {
+  int rc = check_scan_shape(c, lane, n, L, width, height); if (rc) return rc;
+  const size_t bytes = scan_bytes(L, n, width, height);
+  rc = ensure_dev_in(c, std::max((size_t)c->d.p.Ncap * 32, bytes));
   if (rc) return rc;
   char* dst = static_cast<char*>(c->dev_in[0]) + (size_t)lane * c->dev_in_lane_bytes;
-  if (n > 0) CK(cudaMemcpyAsync(dst, pts, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, c->stream));
-  ScanDesc sd; sd.pts = dst; sd.n = n; sd.stride_bytes = stride_bytes; sd.width = width > 0 ? width : 1; sd.height = height;
+  if (bytes > 0) CK(cudaMemcpyAsync(dst, pts, bytes, cudaMemcpyHostToDevice, c->stream));
+  ScanDesc sd; fill_desc(&sd, dst, n, L, width, height);
   CK(cudaMemcpyAsync(c->d.scan + lane, &sd, sizeof(sd), cudaMemcpyHostToDevice, c->stream));
   return 0;
 }
@@ -329,7 +378,9 @@ int liodom_split(liodom_ctx* c, int lane, const void* pts, int n, int stride_byt
                  int32_t* ring_of_point, float* rings_xyzi, int32_t* ring_offsets, int32_t* src_index,
                  int* n_valid, int* n_ambiguous) {
   int rc = check_lane(c, lane); if (rc) return rc;
-  rc = stage_scan(c, lane, pts, n, stride_bytes, width, height); if (rc) return rc;
+  Layout lay;
+  rc = layout_from_stride(c, stride_bytes, &lay); if (rc) return rc;
+  rc = stage_scan(c, lane, pts, n, lay, width, height); if (rc) return rc;
   const DevBuffers& d = c->d;
   c->launches += launch_split(d, c->stream, LaneRange{lane, 1});
   CK(cudaGetLastError());
@@ -351,10 +402,28 @@ int liodom_split(liodom_ctx* c, int lane, const void* pts, int n, int stride_byt
   return 0;
 }
 
+static int extract_impl(liodom_ctx* c, int lane, const void* pts, int n, const Layout& lay, int width, int height,
+                        float* edges_xyzi, int* n_edges, int32_t* edge_ring, int32_t* edge_idx, double* keys);
+
 int liodom_extract(liodom_ctx* c, int lane, const void* pts, int n, int stride_bytes, int width, int height,
                    float* edges_xyzi, int* n_edges, int32_t* edge_ring, int32_t* edge_idx, double* keys) {
   int rc = check_lane(c, lane); if (rc) return rc;
-  rc = stage_scan(c, lane, pts, n, stride_bytes, width, height); if (rc) return rc;
+  Layout lay;
+  rc = layout_from_stride(c, stride_bytes, &lay); if (rc) return rc;
+  return extract_impl(c, lane, pts, n, lay, width, height, edges_xyzi, n_edges, edge_ring, edge_idx, keys);
+}
+
+int liodom_extract_layout(liodom_ctx* c, int lane, const void* data, int n, const liodom_cloud_layout* layout, int width, int height,
+                          float* edges_xyzi, int* n_edges, int32_t* edge_ring, int32_t* edge_idx) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  Layout lay;
+  rc = layout_from_user(c, layout, width, &lay); if (rc) return rc;
+  return extract_impl(c, lane, data, n, lay, width, height, edges_xyzi, n_edges, edge_ring, edge_idx, nullptr);
+}
+
+static int extract_impl(liodom_ctx* c, int lane, const void* pts, int n, const Layout& lay, int width, int height,
+                        float* edges_xyzi, int* n_edges, int32_t* edge_ring, int32_t* edge_idx, double* keys) {
+  int rc = stage_scan(c, lane, pts, n, lay, width, height); if (rc) return rc;
   const DevBuffers& d = c->dprod;
   if (keys) CK(cudaMemsetAsync(d.keys + (size_t)lane * d.p.Ncap, 0xff, sizeof(double) * d.p.Ncap, c->stream));  // NaN
   c->launches += launch_split(d, c->stream, LaneRange{lane, 1});
@@ -623,48 +692,61 @@ int liodom_register(liodom_ctx* c, int lane, const float* edges_xyzi, int n_edge
 }
 
 // ---- whole hot path, batched --------------------------------------------------------------
+static int scan_batch_impl(liodom_ctx* c, const void* const* pts, const int* n, const Layout& lay, int width, int height, int on_device);
+
 int liodom_scan_batch(liodom_ctx* c, const void* const* pts, const int* n, int stride_bytes, int width, int height, int on_device) {
   if (!c) return LIODOM_E_INVALID;
+  Layout lay;
+  int rc = layout_from_stride(c, stride_bytes, &lay); if (rc) return rc;
+  return scan_batch_impl(c, pts, n, lay, width, height, on_device);
+}
+
+int liodom_scan_batch_layout(liodom_ctx* c, const void* const* data, const int* n, const liodom_cloud_layout* layout, int width, int height, int on_device) {
+  if (!c) return LIODOM_E_INVALID;
+  Layout lay;
+  int rc = layout_from_user(c, layout, width, &lay); if (rc) return rc;
+  return scan_batch_impl(c, data, n, lay, width, height, on_device);
+}
+
+static int scan_batch_impl(liodom_ctx* c, const void* const* pts, const int* n, const Layout& lay, int width, int height, int on_device) {
   CK(cudaSetDevice(c->device));
-  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(c, LIODOM_E_INVALID, "bad stride_bytes %d", stride_bytes);
   const int B = c->batch;
-  for (int l = 0; l < B; ++l) {
-    if (n[l] < 0 || n[l] > c->d.p.Ncap) return fail(c, LIODOM_E_CAPACITY, "lane %d: %d points exceed max_points capacity %d", l, n[l], c->d.p.Ncap);
-    if (c->params.lidar_type == 1 && ((long long)width * height != n[l] || height > c->params.scan_lines))
-      return fail(c, LIODOM_E_INVALID, "lane %d: organised cloud needs width*height == n and height <= scan_lines", l);
-  }
-  int rc = hash_generation_guard(c, 1); if (rc) return rc;
+  int rc;
+  for (int l = 0; l < B; ++l) { rc = check_scan_shape(c, l, n[l], lay, width, height); if (rc) return rc; }
+  rc = hash_generation_guard(c, 1); if (rc) return rc;
   const int buf = c->cur ^ 1;
   if (c->in_flight[buf]) { CK(cudaEventSynchronize(c->ev_done[buf])); c->in_flight[buf] = false; }
   ScanDesc* hd = c->h_desc[buf];
   if (!on_device) {
-    rc = ensure_dev_in(c, (size_t)c->d.p.Ncap * 32); if (rc) return rc;
+    size_t max_bytes = (size_t)c->d.p.Ncap * 32;
+    for (int l = 0; l < B; ++l) max_bytes = std::max(max_bytes, scan_bytes(lay, n[l], width, height));
+    rc = ensure_dev_in(c, max_bytes); if (rc) return rc;
     // Host scans laid out back to back (a batching front-end would do that) go over PCIe as ONE copy
     // into a packed staging area; otherwise one copy per lane into fixed-pitch slots.
-    bool packed = B > 1 && (stride_bytes & 15) == 0;
+    bool packed = B > 1 && (lay.step & 15) == 0 && !lay.row_step;
     size_t total = 0;
     for (int l = 0; l < B && packed; ++l) {
       if (static_cast<const char*>(pts[l]) != static_cast<const char*>(pts[0]) + total) packed = false;
-      total += (size_t)n[l] * stride_bytes;
+      total += (size_t)n[l] * lay.step;
     }
     if (packed && total <= c->dev_in_bytes) {
       char* dst = static_cast<char*>(c->dev_in[buf]);
       if (total > 0) CK(cudaMemcpyAsync(dst, pts[0], total, cudaMemcpyHostToDevice, c->copy_stream));
       size_t off = 0;
-      for (int l = 0; l < B; ++l) { hd[l].pts = dst + off; off += (size_t)n[l] * stride_bytes; }
+      for (int l = 0; l < B; ++l) { fill_desc(&hd[l], dst + off, n[l], lay, width, height); off += (size_t)n[l] * lay.step; }
     } else {
       for (int l = 0; l < B; ++l) {
         char* dst = static_cast<char*>(c->dev_in[buf]) + (size_t)l * c->dev_in_lane_bytes;
-        if (n[l] > 0) CK(cudaMemcpyAsync(dst, pts[l], (size_t)n[l] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-        hd[l].pts = dst;
+        const size_t bytes = scan_bytes(lay, n[l], width, height);
+        if (bytes > 0) CK(cudaMemcpyAsync(dst, pts[l], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        fill_desc(&hd[l], dst, n[l], lay, width, height);
       }
     }
     CK(cudaEventRecord(c->ev_copied[buf], c->copy_stream));
     CK(cudaStreamWaitEvent(c->stream, c->ev_copied[buf], 0));
   } else {
-    for (int l = 0; l < B; ++l) hd[l].pts = pts[l];
+    for (int l = 0; l < B; ++l) fill_desc(&hd[l], pts[l], n[l], lay, width, height);
   }
-  for (int l = 0; l < B; ++l) { hd[l].n = n[l]; hd[l].stride_bytes = stride_bytes; hd[l].width = width > 0 ? width : 1; hd[l].height = height; }
   const DevBuffers& d = c->dprod;
   CK(cudaMemcpyAsync(d.scan, hd, sizeof(ScanDesc) * B, cudaMemcpyHostToDevice, c->stream));
   const LaneRange lr{0, B};

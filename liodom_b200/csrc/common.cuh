@@ -54,8 +54,13 @@ struct DevParams {
 struct ScanDesc {
   const void* pts;
   int n;
-  int stride_bytes;
+  int stride_bytes;       // point_step
   int width, height;
+  // generic sensor_msgs/PointCloud2 layouts (liodom_cloud_layout); generic == 0: x,y,z at 0,4,8 and
+  // intensity at +16 (stride >= 32) or +12, rows back to back
+  int generic;
+  int row_step;           // bytes per row (generic layouts with padded rows), else 0
+  int off_x, off_y, off_z, off_i;   // byte offsets of the FLOAT32 fields; off_i < 0: no intensity
 };
 
 // Sliding window bookkeeping (LocalMapManager, src/laser_odometry.cc:24-69).

@@ -12,9 +12,23 @@ namespace liodom {
 // ---------------------------------------------------------------------------------------
 // A1 + A2: isValidPoint + ring id (src/feature_extractor.cc:84-102, :126-151, :160-175)
 // ---------------------------------------------------------------------------------------
+// FLOAT32 field at an arbitrary byte address (PointCloud2 point_step need not be a multiple of 4,
+// e.g. the 22-byte velodyne PointXYZIRT): little-endian bytes, as pcl::fromROSMsg's memcpy reads them.
+__device__ __forceinline__ float load_f32_bytes(const char* p) {
+  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) return __ldg(reinterpret_cast<const float*>(p));
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
+  return __uint_as_float((unsigned)__ldg(b) | ((unsigned)__ldg(b + 1) << 8) | ((unsigned)__ldg(b + 2) << 16) | ((unsigned)__ldg(b + 3) << 24));
+}
+__device__ __forceinline__ const char* point_base(const ScanDesc& sc, int i) {
+  const char* base = reinterpret_cast<const char*>(sc.pts);
+  if (sc.generic && sc.row_step) return base + (size_t)(i / sc.width) * sc.row_step + (size_t)(i % sc.width) * sc.stride_bytes;
+  return base + (size_t)i * sc.stride_bytes;
+}
 __device__ __forceinline__ void load_xyz(const ScanDesc& sc, int i, float& x, float& y, float& z) {
-  const char* base = reinterpret_cast<const char*>(sc.pts) + (size_t)i * sc.stride_bytes;
-  if ((sc.stride_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(sc.pts) & 15) == 0) {
+  const char* base = point_base(sc, i);
+  if (sc.generic) {
+    x = load_f32_bytes(base + sc.off_x); y = load_f32_bytes(base + sc.off_y); z = load_f32_bytes(base + sc.off_z);
+  } else if ((sc.stride_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(sc.pts) & 15) == 0) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(base));
     x = v.x; y = v.y; z = v.z;
   } else {
@@ -23,10 +37,15 @@ __device__ __forceinline__ void load_xyz(const ScanDesc& sc, int i, float& x, fl
   }
 }
 __device__ __forceinline__ float4 load_xyzi(const ScanDesc& sc, int i) {
-  const char* base = reinterpret_cast<const char*>(sc.pts) + (size_t)i * sc.stride_bytes;
+  const char* base = point_base(sc, i);
+  float4 v;
+  if (sc.generic) {
+    v.x = load_f32_bytes(base + sc.off_x); v.y = load_f32_bytes(base + sc.off_y); v.z = load_f32_bytes(base + sc.off_z);
+    v.w = sc.off_i >= 0 ? load_f32_bytes(base + sc.off_i) : 0.f;
+    return v;
+  }
   // pcl::PointXYZI keeps intensity in the second 16-byte half (data_c[0]); packed records at +12.
   const int ioff = sc.stride_bytes >= 32 ? 16 : 12;
-  float4 v;
   if ((sc.stride_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(sc.pts) & 15) == 0) {
     v = __ldg(reinterpret_cast<const float4*>(base));
     if (ioff != 12) v.w = __ldg(reinterpret_cast<const float*>(base + ioff));

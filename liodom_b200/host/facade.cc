@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <thread>
 
 namespace liodom {
@@ -210,14 +211,63 @@ bool FeatureExtractor::ensureContext(size_t npoints) {
   return (bool)ctx_;
 }
 
+// ---- sensor_msgs/PointCloud2 -> liodom::Point (pcl::fromROSMsg, src/liodom_node.cc:43-44, :62-63) ----
+bool cloudLayoutFromFields(const PointCloud2& msg, liodom_cloud_layout* layout) {
+  if (!layout || msg.is_bigendian) return false;
+  int off[4] = {-1, -1, -1, -1};
+  static const char* names[4] = {"x", "y", "z", "intensity"};
+  for (const PointField& f : msg.fields)
+    for (int k = 0; k < 4; ++k)
+      if (off[k] < 0 && f.name == names[k] && f.datatype == PointField::FLOAT32 && f.count == 1) off[k] = (int)f.offset;
+  if (off[0] < 0 || off[1] < 0 || off[2] < 0) return false;
+  layout->point_step = (int)msg.point_step; layout->row_step = (int)msg.row_step;
+  layout->off_x = off[0]; layout->off_y = off[1]; layout->off_z = off[2]; layout->off_intensity = off[3];
+  layout->is_bigendian = 0;
+  return true;
+}
+
+bool fromROSMsg(const PointCloud2& msg, PointCloud& cloud) {
+  liodom_cloud_layout lay;
+  cloud.clear(); cloud.raw.reset();
+  if (!cloudLayoutFromFields(msg, &lay)) { LIODOM_ERROR("fromROSMsg: no FLOAT32 x/y/z fields (or a big-endian message)"); return false; }
+  const size_t row = msg.row_step ? msg.row_step : (size_t)msg.width * msg.point_step;
+  if (msg.data.size() < (size_t)msg.height * row) { LIODOM_ERROR("fromROSMsg: data shorter than height * row_step"); return false; }
+  cloud.points.resize((size_t)msg.width * msg.height);
+  for (uint32_t r = 0; r < msg.height; ++r)
+    for (uint32_t c = 0; c < msg.width; ++c) {
+      const uint8_t* src = msg.data.data() + r * row + (size_t)c * msg.point_step;
+      Point& p = cloud.points[(size_t)r * msg.width + c];
+      std::memcpy(&p.x, src + lay.off_x, 4); std::memcpy(&p.y, src + lay.off_y, 4); std::memcpy(&p.z, src + lay.off_z, 4);
+      if (lay.off_intensity >= 0) std::memcpy(&p.intensity, src + lay.off_intensity, 4);
+    }
+  cloud.width = msg.width; cloud.height = msg.height; cloud.is_dense = msg.is_dense; cloud.header = msg.header;
+  return true;
+}
+
+bool fromROSMsgDeferred(const PointCloud2::ConstPtr& msg, PointCloud& cloud) {
+  liodom_cloud_layout lay;
+  cloud.clear(); cloud.raw.reset();
+  if (!msg || !cloudLayoutFromFields(*msg, &lay)) { LIODOM_ERROR("fromROSMsgDeferred: no FLOAT32 x/y/z fields (or a big-endian message)"); return false; }
+  cloud.raw = msg;
+  cloud.width = msg->width; cloud.height = msg->height; cloud.is_dense = msg->is_dense; cloud.header = msg->header;
+  return true;
+}
+
 bool FeatureExtractor::extract(const PointCloud::Ptr& pc_curr, PointCloud::Ptr& pc_edges) {
   if (!ensureContext(pc_curr->size())) return false;
   const int cap = liodom_max_edges(ctx_.get());
   std::vector<float> edges((size_t)cap * 4);
   int ne = 0;
   const int w = params->lidar_type_ == 1 ? (int)pc_curr->width : 0, h = params->lidar_type_ == 1 ? (int)pc_curr->height : 0;
-  const int rc = liodom_extract(ctx_.get(), 0, pc_curr->points.data(), (int)pc_curr->size(), (int)sizeof(Point), w, h,
-                                edges.data(), &ne, nullptr, nullptr, nullptr);
+  int rc;
+  if (pc_curr->raw) {   // message bytes straight to the device (no host-side decode)
+    liodom_cloud_layout lay;
+    if (!cloudLayoutFromFields(*pc_curr->raw, &lay)) { LIODOM_ERROR("extract: unusable PointCloud2 field list"); return false; }
+    const int ww = (w > 0 || lay.row_step) ? (int)pc_curr->raw->width : 0, hh = (h > 0 || lay.row_step) ? (int)pc_curr->raw->height : 0;
+    rc = liodom_extract_layout(ctx_.get(), 0, pc_curr->raw->data.data(), (int)pc_curr->size(), &lay, ww, hh, edges.data(), &ne, nullptr, nullptr);
+  } else
+    rc = liodom_extract(ctx_.get(), 0, pc_curr->points.data(), (int)pc_curr->size(), (int)sizeof(Point), w, h,
+                        edges.data(), &ne, nullptr, nullptr, nullptr);
   if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_extract failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
   cloud_from_xyzi(edges.data(), ne, pc_edges.get());
   return true;
@@ -415,7 +465,9 @@ struct liodom_host_options {
 
 // scans: concatenated float32 x,y,z,intensity; npts[nframes]. poses_out: nframes x 16 (row-major).
 // Returns the number of poses produced, or a negative value on setup failure.
-int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans, const int* npts, int nframes,
+}  // extern "C"
+
+static int run_sequence_impl(const liodom_host_options* opt, int nframes, const std::function<liodom::PointCloud::Ptr(int)>& make_cloud,
                              double* poses_out, int* nfeats_out, const char* results_dir) {
   using namespace liodom;
   NodeHandle nh;
@@ -439,18 +491,8 @@ int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans,
   std::atomic<bool> running(true);
   std::thread fext_thread(fext, std::ref(running));
   std::thread lodom_thread(lodom, std::ref(running));
-  size_t pos = 0;
   for (int f = 0; f < nframes; ++f) {   // lidarClb (src/liodom_node.cc:40-55)
-    PointCloud::Ptr pc(new PointCloud);
-    pc->points.resize((size_t)npts[f]);
-    for (int i = 0; i < npts[f]; ++i) {
-      Point& q = pc->points[(size_t)i];
-      const float* s = scans + (pos + (size_t)i) * 4;
-      q.x = s[0]; q.y = s[1]; q.z = s[2]; q.intensity = s[3];
-    }
-    pos += (size_t)npts[f];
-    pc->width = opt->lidar_type == 1 ? (uint32_t)opt->width : (uint32_t)npts[f];
-    pc->height = opt->lidar_type == 1 ? (uint32_t)opt->height : 1;
+    PointCloud::Ptr pc = make_cloud(f);
     Header h; h.seq = (uint32_t)f; h.stamp.secs = 0.1 * f; h.frame_id = "laser";
     stats->startFrame(Clock::now());
     sdata->pushPointCloud(pc, h);
@@ -469,6 +511,58 @@ int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans,
   if (nfeats_out) std::memcpy(nfeats_out, nf.data(), sizeof(int) * (size_t)nframes);
   if (results_dir && results_dir[0]) stats->writeResults(results_dir);
   return produced.load();
+}
+
+extern "C" {
+
+int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans, const int* npts, int nframes,
+                             double* poses_out, int* nfeats_out, const char* results_dir) {
+  using namespace liodom;
+  std::vector<size_t> start((size_t)nframes + 1, 0);
+  for (int f = 0; f < nframes; ++f) start[f + 1] = start[f] + (size_t)npts[f];
+  return run_sequence_impl(opt, nframes, [&](int f) {
+    PointCloud::Ptr pc(new PointCloud);
+    pc->points.resize((size_t)npts[f]);
+    for (int i = 0; i < npts[f]; ++i) {
+      Point& q = pc->points[(size_t)i];
+      const float* s = scans + (start[f] + (size_t)i) * 4;
+      q.x = s[0]; q.y = s[1]; q.z = s[2]; q.intensity = s[3];
+    }
+    pc->width = opt->lidar_type == 1 ? (uint32_t)opt->width : (uint32_t)npts[f];
+    pc->height = opt->lidar_type == 1 ? (uint32_t)opt->height : 1;
+    return pc;
+  }, poses_out, nfeats_out, results_dir);
+}
+
+// The same with sensor_msgs/PointCloud2 messages, as lidarClb receives them: `data` holds the frames'
+// blobs back to back (frame f: height[f] * row_step bytes), `field_names` is a comma-separated list
+// matching field_offsets / field_datatypes.  The bytes are never decoded on the host.
+int liodom_host_run_sequence_msgs(const liodom_host_options* opt, const unsigned char* data, const int* widths, const int* heights,
+                                  int nframes, int point_step, int row_pad, const char* field_names, const int* field_offsets,
+                                  const int* field_datatypes, int nfields, double* poses_out, int* nfeats_out, const char* results_dir) {
+  using namespace liodom;
+  std::vector<PointField> fields;
+  std::string names(field_names ? field_names : "");
+  size_t p0 = 0;
+  for (int k = 0; k < nfields; ++k) {
+    const size_t p1 = names.find(',', p0);
+    PointField f;
+    f.name = names.substr(p0, p1 == std::string::npos ? std::string::npos : p1 - p0);
+    f.offset = (uint32_t)field_offsets[k]; f.datatype = (uint8_t)field_datatypes[k]; f.count = 1;
+    fields.push_back(f);
+    p0 = p1 == std::string::npos ? names.size() : p1 + 1;
+  }
+  std::vector<size_t> start((size_t)nframes + 1, 0);
+  for (int f = 0; f < nframes; ++f) start[f + 1] = start[f] + (size_t)heights[f] * ((size_t)widths[f] * point_step + row_pad);
+  return run_sequence_impl(opt, nframes, [&](int f) {
+    PointCloud2::Ptr msg(new PointCloud2);
+    msg->width = (uint32_t)widths[f]; msg->height = (uint32_t)heights[f]; msg->fields = fields;
+    msg->point_step = (uint32_t)point_step; msg->row_step = (uint32_t)(widths[f] * point_step + row_pad);
+    msg->data.assign(data + start[f], data + start[f + 1]);
+    PointCloud::Ptr pc(new PointCloud);
+    fromROSMsgDeferred(msg, *pc);
+    return pc;
+  }, poses_out, nfeats_out, results_dir);
 }
 
 }  // extern "C"

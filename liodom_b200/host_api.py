@@ -39,3 +39,31 @@ def run_sequence(scans, results_dir="", lockstep=True, width=0, height=0, **kw):
     produced = lib.liodom_host_run_sequence(ctypes.byref(o), pts.ctypes.data_as(vp), npts.ctypes.data_as(vp), len(scans),
                                             poses.ctypes.data_as(vp), nf.ctypes.data_as(vp), results_dir.encode())
     return poses.reshape(-1, 4, 4), nf, produced
+
+
+FLOAT32, UINT16, FLOAT64 = 7, 4, 8   # sensor_msgs/PointField datatypes
+
+
+def run_sequence_msgs(blobs, widths, heights, point_step, fields, row_pad=0, results_dir="", lockstep=True, **kw):
+    """Like run_sequence, but every frame is a raw sensor_msgs/PointCloud2 data blob (uint8 array of
+    height * (width * point_step + row_pad) bytes) and `fields` = [(name, offset, datatype), ...].
+    The façade derives the layout by pcl::fromROSMsg's rules and ships the bytes to the GPU undecoded."""
+    lib = load()
+    lib.liodom_host_run_sequence_msgs.restype = ctypes.c_int
+    o = HostOptions(kw.get("min_range", 3.0), kw.get("max_range", 75.0), kw.get("lidar_type", 0), kw.get("scan_lines", 64),
+                    kw.get("scan_regions", 8), kw.get("edges_per_region", 10), kw.get("prev_frames", 5), int(kw.get("mapping", 0)),
+                    0, 0, 1 if lockstep else 0)
+    data = np.ascontiguousarray(np.concatenate([np.asarray(b, np.uint8).ravel() for b in blobs]))
+    w = np.array(widths, np.int32)
+    h = np.array(heights, np.int32)
+    offs = np.array([f[1] for f in fields], np.int32)
+    dts = np.array([f[2] for f in fields], np.int32)
+    names = ",".join(f[0] for f in fields).encode()
+    n = len(blobs)
+    poses = np.zeros((n, 16))
+    nf = np.zeros(n, np.int32)
+    vp = ctypes.c_void_p
+    produced = lib.liodom_host_run_sequence_msgs(ctypes.byref(o), data.ctypes.data_as(vp), w.ctypes.data_as(vp), h.ctypes.data_as(vp), n,
+                                                 point_step, row_pad, names, offs.ctypes.data_as(vp), dts.ctypes.data_as(vp), len(fields),
+                                                 poses.ctypes.data_as(vp), nf.ctypes.data_as(vp), results_dir.encode())
+    return poses.reshape(-1, 4, 4), nf, produced

@@ -240,6 +240,14 @@ class LocalMapManager:
         lib().orc_lmap_set_max_frames(self.h, int(n))
 
 
+def decode_cloud2(data, width, height, point_step, row_step, off_x, off_y, off_z, off_i):
+    """pcl::fromROSMsg<PointXYZI> of a raw sensor_msgs/PointCloud2 blob -> [n,4] float32."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.empty((width * height, 4), np.float32)
+    lib().orc_decode_cloud2(_p(data), width, height, point_step, row_step, off_x, off_y, off_z, off_i, _p(out))
+    return out
+
+
 def voxelgrid(pts, leaf):
     pts = _f4(pts)
     out = np.empty_like(pts)

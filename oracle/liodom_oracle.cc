@@ -1100,6 +1100,18 @@ int orc_lmap_frames(const OrcLmap* m) { return (int)m->nframes; }
 void orc_lmap_get(const OrcLmap* m, float* xyzi) { std::memcpy(xyzi, m->total_points.data(), m->total_points.size() * 16); }
 void orc_lmap_set_max_frames(OrcLmap* m, int max_frames) { m->max_nframes = (size_t)max_frames; }
 
+void orc_decode_cloud2(const uint8_t* data, int width, int height, int point_step, int row_step,
+                       int off_x, int off_y, int off_z, int off_i, float* out_xyzi) {
+  for (int r = 0; r < height; ++r)
+    for (int c = 0; c < width; ++c) {
+      const uint8_t* src = data + (size_t)r * row_step + (size_t)c * point_step;
+      float* o = out_xyzi + ((size_t)r * width + c) * 4;
+      std::memcpy(o, src + off_x, 4); std::memcpy(o + 1, src + off_y, 4); std::memcpy(o + 2, src + off_z, 4);
+      o[3] = 0.f;
+      if (off_i >= 0) std::memcpy(o + 3, src + off_i, 4);
+    }
+}
+
 int orc_voxelgrid(const float* in_xyzi, int n, float leaf, float* out_xyzi) {
   std::vector<P4> in(reinterpret_cast<const P4*>(in_xyzi), reinterpret_cast<const P4*>(in_xyzi) + n), out;
   int r = voxel_grid(in, leaf, out);

@@ -159,6 +159,13 @@ void orc_map_get(const OrcMap* m, float* xyzi);
 void orc_map_cell_info(const OrcMap* m, int i, int32_t* key3, int32_t* count);
 int orc_map_get_local(const OrcMap* m, const double* T, int cells_xy, int cells_z, float* xyzi, int cap);
 
+/* pcl::fromROSMsg<PointXYZI> (call sites src/liodom_node.cc:43-44, :62-63; PCL 1.10
+ * pcl/conversions.h fromPCLPointCloud2, third-party): per point, each matched FLOAT32 field is
+ * memcpy'd from data + row * row_step + col * point_step + offset; an unmatched intensity
+ * stays 0 (off_i < 0).  out_xyzi: width * height x 4 floats. */
+void orc_decode_cloud2(const uint8_t* data, int width, int height, int point_step, int row_step,
+                       int off_x, int off_y, int off_z, int off_i, float* out_xyzi);
+
 /* Whole-path CPU baseline: for each of nframes scans (concatenated, counts in npts):
  * split -> extract -> odometry.  poses_out nframes x 16.  stage_us[5] accumulates
  * {split, extract, associate, solve, window}. Returns total edges. */
