@@ -135,6 +135,17 @@ struct Isometry3d {      // the part of Eigen::Isometry3d the reference uses
 
 /* Parameter source standing in for ros::NodeHandle's private-parameter lookup
  * (nh.param(name, out, default), src/params.cc:40-108). */
+/* nav_msgs/Odometry + geometry_msgs/TwistStamped content filled by LaserOdometer::publishOdom
+ * (src/laser_odometry.cc:395-446); the TF broadcast carries the same position / orientation. */
+struct Odometry {
+  Header header;               // frame_id = fixed_frame, stamp = the scan's
+  std::string child_frame_id;  // base_frame
+  Quaterniond orientation;     // of base_link in the fixed frame
+  double position[3] = {0, 0, 0};
+  double twist_linear[3] = {0, 0, 0};
+  double twist_angular[3] = {0, 0, 0};
+};
+
 class NodeHandle {
  public:
   NodeHandle() {}

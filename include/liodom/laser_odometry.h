@@ -44,6 +44,14 @@ class LaserOdometer {
   bool process(const PointCloud::Ptr& feats, const Header& header, Isometry3d* pose_out);
   /* stands in for publishOdom (src/laser_odometry.cc:395-446): header + odom_ (laser frame) */
   void setOdomCallback(std::function<void(const Header&, const Isometry3d&)> cb) { odom_cb_ = cb; }
+  /* the messages publishOdom assembles (odometry in base_link + twist); called once per frame */
+  void setOdometryMsgCallback(std::function<void(const Odometry&)> cb) { odom_msg_cb_ = cb; }
+  /* stands in for getBaseToLaserTf (src/laser_odometry.cc:368-393): the static laser->base transform */
+  void setLaserToBase(const Isometry3d& laser_to_base);
+  /* publishOdom's arithmetic (src/laser_odometry.cc:395-432) */
+  static Odometry makeOdometry(const Header& header, const Isometry3d& pose, const Isometry3d& prev_odom,
+                               const Isometry3d& laser_to_base, double prev_stamp, const std::string& fixed_frame,
+                               const std::string& base_frame);
 
  private:
   NodeHandle nh_;
@@ -54,7 +62,11 @@ class LaserOdometer {
   Params* params;
   std::shared_ptr<liodom_ctx> ctx_;
   std::function<void(const Header&, const Isometry3d&)> odom_cb_;
+  std::function<void(const Odometry&)> odom_msg_cb_;
+  Isometry3d prev_odom_, laser_to_base_;
+  double prev_stamp_ = 0.0;
   bool ensureContext();
+  void publishOdom(const Header& header, const Isometry3d& pose);
 };
 
 }  // namespace liodom

@@ -47,6 +47,7 @@ typedef struct liodom_params {
   int mapping;            /* 0 */
   int max_points;         /* capacity: points per scan (default 262144) */
   int max_received_map;   /* capacity: points of the received local map (mapping=1) */
+  int use_imu;            /* 0; 1: roll/pitch of the predicted pose come from the IMU (src/laser_odometry.cc:152-183) */
 } liodom_params;
 
 typedef struct liodom_ctx liodom_ctx;
@@ -120,6 +121,12 @@ int liodom_commit_received_map(liodom_ctx* ctx, int lane, int n);
 int liodom_odom_reset(liodom_ctx* ctx, int lane);
 int liodom_odom_set_pose(liodom_ctx* ctx, int lane, const double* odom16, const double* prev_odom16);
 int liodom_odom_get_pose(liodom_ctx* ctx, int lane, double* odom16, double* prev_odom16);
+
+/* use_imu inputs: the latest IMU orientation (x,y,z,w), i.e. SharedData::setLastIMUOri fed by imuClb
+ * (src/liodom_node.cc:66-70), and laser_to_base_ as cached by getBaseToLaserTf (src/laser_odometry.cc:368-393;
+ * row-major 4x4, identity until set). */
+int liodom_odom_set_imu(liodom_ctx* ctx, int lane, const double* q_xyzw);
+int liodom_odom_set_laser_to_base(liodom_ctx* ctx, int lane, const double* T16);
 
 typedef struct liodom_solve_summary {
   int iterations;

@@ -18,7 +18,7 @@ class Params(ctypes.Structure):
     _fields_ = [("min_range", ctypes.c_double), ("max_range", ctypes.c_double), ("lidar_type", ctypes.c_int),
                 ("scan_lines", ctypes.c_int), ("scan_regions", ctypes.c_int), ("edges_per_region", ctypes.c_int),
                 ("prev_frames", ctypes.c_int), ("filter_local_map", ctypes.c_int), ("mapping", ctypes.c_int),
-                ("max_points", ctypes.c_int), ("max_received_map", ctypes.c_int)]
+                ("max_points", ctypes.c_int), ("max_received_map", ctypes.c_int), ("use_imu", ctypes.c_int)]
 
 
 class CloudLayout(ctypes.Structure):
@@ -229,6 +229,14 @@ class Context:
         o = np.ascontiguousarray(odom, dtype=np.float64).reshape(16)
         q = np.ascontiguousarray(prev_odom, dtype=np.float64).reshape(16)
         self._ck(self.lib.liodom_odom_set_pose(self.h, lane, _p(o), _p(q)))
+
+    def set_imu(self, q_xyzw, lane=0):
+        q = np.ascontiguousarray(q_xyzw, dtype=np.float64)
+        self._ck(self.lib.liodom_odom_set_imu(self.h, lane, _p(q)))
+
+    def set_laser_to_base(self, T, lane=0):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        self._ck(self.lib.liodom_odom_set_laser_to_base(self.h, lane, _p(T)))
 
     def get_pose(self, lane=0):
         o = np.empty(16)

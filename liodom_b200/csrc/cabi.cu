@@ -118,7 +118,7 @@ extern "C" {
 void liodom_default_params(liodom_params* p) {
   p->min_range = 3.0; p->max_range = 75.0; p->lidar_type = 0; p->scan_lines = 64; p->scan_regions = 8;
   p->edges_per_region = 10; p->prev_frames = 5; p->filter_local_map = 0; p->mapping = 0;
-  p->max_points = 262144; p->max_received_map = 0;
+  p->max_points = 262144; p->max_received_map = 0; p->use_imu = 0;
 }
 
 const char* liodom_last_error(const liodom_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -169,7 +169,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   DevParams& p = d.p;
   p.min_range = P.min_range; p.max_range = P.max_range; p.lidar_type = P.lidar_type; p.scan_lines = P.scan_lines;
   p.scan_regions = P.scan_regions; p.edges_per_region = P.edges_per_region; p.prev_frames = P.prev_frames;
-  p.filter_local_map = P.filter_local_map; p.mapping = P.mapping;
+  p.filter_local_map = P.filter_local_map; p.mapping = P.mapping; p.use_imu = P.use_imu;
   p.batch = batch;
   p.Ncap = (P.max_points + kChunk - 1) / kChunk * kChunk;
   p.chunks = p.Ncap / kChunk;
@@ -249,6 +249,8 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
     os[l].odom[0] = os[l].odom[5] = os[l].odom[10] = 1.0;
     os[l].prev[0] = os[l].prev[5] = os[l].prev[10] = 1.0;
     os[l].q[3] = 1.0;
+    os[l].imu_q[3] = 1.0;
+    os[l].l2b[0] = os[l].l2b[5] = os[l].l2b[10] = 1.0;
     ws[l].max_frames = P.prev_frames;
   }
   CKC(cudaMemcpyAsync(d.ostate, os.data(), sizeof(OdomState) * B, cudaMemcpyHostToDevice, c->stream));
@@ -531,6 +533,7 @@ int liodom_odom_reset(liodom_ctx* c, int lane) {
   int rc = check_lane(c, lane); if (rc) return rc;
   OdomState os; std::memset(&os, 0, sizeof(os));
   os.odom[0] = os.odom[5] = os.odom[10] = 1.0; os.prev[0] = os.prev[5] = os.prev[10] = 1.0; os.q[3] = 1.0;
+  os.imu_q[3] = 1.0; os.l2b[0] = os.l2b[5] = os.l2b[10] = 1.0;
   CK(cudaMemcpyAsync(c->d.ostate + lane, &os, sizeof(os), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return liodom_lmap_clear(c, lane);
@@ -545,6 +548,22 @@ int liodom_odom_set_pose(liodom_ctx* c, int lane, const double* odom16, const do
   if (prev16) pose12_from16(prev16, os.prev);
   os.init = 1;
   CK(cudaMemcpyAsync(c->d.ostate + lane, &os, sizeof(os), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int liodom_odom_set_imu(liodom_ctx* c, int lane, const double* q_xyzw) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  if (!q_xyzw) return fail(c, LIODOM_E_INVALID, "q_xyzw is NULL");
+  CK(cudaMemcpyAsync(c->d.ostate[lane].imu_q, q_xyzw, sizeof(double) * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));   // the caller's buffer may be a temporary
+  return 0;
+}
+
+int liodom_odom_set_laser_to_base(liodom_ctx* c, int lane, const double* T16) {
+  int rc = check_lane(c, lane); if (rc) return rc;
+  if (!T16) return fail(c, LIODOM_E_INVALID, "T16 is NULL");
+  CK(cudaMemcpyAsync(c->d.ostate[lane].l2b, T16, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

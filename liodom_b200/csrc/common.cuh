@@ -40,7 +40,7 @@ struct __align__(16) HashEntry {
 struct DevParams {
   double min_range, max_range;
   int lidar_type, scan_lines, scan_regions, edges_per_region;
-  int prev_frames, filter_local_map, mapping;
+  int prev_frames, filter_local_map, mapping, use_imu;
   int Ncap, Ecap, Mcap, Hcap, Rcap;  // Rcap: received-map capacity
   int slots;                         // window slabs allocated
   int chunks;                        // ceil(Ncap / kChunk)
@@ -100,6 +100,10 @@ struct OdomState {
   int n_valid;            // valid points of the last split
   int n_ambiguous;
   int pad;
+  // use_imu (src/laser_odometry.cc:152-183): latest IMU orientation (x,y,z,w; SharedData::setLastIMUOri)
+  // and the cached base->laser transform laser_to_base_ (:368-393), row-major 3x4
+  double imu_q[4];
+  double l2b[12];
 };
 
 struct SolveSummaryDev {

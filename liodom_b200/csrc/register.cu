@@ -166,6 +166,78 @@ __device__ void quat_from_matrix(const double* A, double* q) {
 #undef M_
 }
 
+// ---- use_imu: roll and pitch of the predicted pose (base_link frame) replaced by the IMU's
+// (src/laser_odometry.cc:152-183).  tf::Matrix3x3 / tf::Quaternion algebra restated (tf LinearMath,
+// third-party): setRotation, getRPY (getEulerYPR solution 1), setRPY (setEulerYPR), getRotation.
+__device__ void tf_matrix_from_quat(const double* q /*x,y,z,w*/, double* m /*3x3*/) {
+  const double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const double s = 2.0 / d;
+  const double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+  const double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+  const double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+  m[0] = 1.0 - (yy + zz); m[1] = xy - wz; m[2] = xz + wy;
+  m[3] = xy + wz; m[4] = 1.0 - (xx + zz); m[5] = yz - wx;
+  m[6] = xz - wy; m[7] = yz + wx; m[8] = 1.0 - (xx + yy);
+}
+__device__ void tf_get_rpy(const double* m, double* roll, double* pitch, double* yaw) {
+  const double kPi = 3.14159265358979323846;
+  if (fabs(m[6]) >= 1.0) {   // gimbal lock
+    *yaw = 0.0;
+    if (m[6] < 0.0) { *pitch = kPi / 2.0; *roll = atan2(m[1], m[2]); }
+    else { *pitch = -kPi / 2.0; *roll = atan2(-m[1], -m[2]); }
+  } else {
+    *pitch = -asin(m[6]);
+    const double cp = cos(*pitch);
+    *roll = atan2(m[7] / cp, m[8] / cp);
+    *yaw = atan2(m[3] / cp, m[0] / cp);
+  }
+}
+__device__ void tf_set_rpy(double roll, double pitch, double yaw, double* m) {
+  const double ci = cos(roll), cj = cos(pitch), ch = cos(yaw), si = sin(roll), sj = sin(pitch), sh = sin(yaw);
+  const double cc = ci * ch, cs = ci * sh, sc = si * ch, ss = si * sh;
+  m[0] = cj * ch; m[1] = sj * sc - cs; m[2] = sj * cc + ss;
+  m[3] = cj * sh; m[4] = sj * ss + cc; m[5] = sj * cs - sc;
+  m[6] = -sj; m[7] = cj * si; m[8] = cj * ci;
+}
+__device__ void tf_get_rotation(const double* m, double* q /*x,y,z,w*/) {
+  const double trace = m[0] + m[4] + m[8];
+  if (trace > 0.0) {
+    double s = sqrt(trace + 1.0);
+    q[3] = s * 0.5; s = 0.5 / s;
+    q[0] = (m[7] - m[5]) * s; q[1] = (m[2] - m[6]) * s; q[2] = (m[3] - m[1]) * s;
+  } else {
+    const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+    q[i] = s * 0.5; s = 0.5 / s;
+    q[3] = (m[k * 3 + j] - m[j * 3 + k]) * s; q[j] = (m[j * 3 + i] + m[i * 3 + j]) * s; q[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+  }
+}
+__device__ void imu_override(OdomState& os) {
+  double imu_m[9], r_imu, p_imu, y_imu;
+  tf_matrix_from_quat(os.imu_q, imu_m);
+  tf_get_rpy(imu_m, &r_imu, &p_imu, &y_imu);
+  double bl[12], q[4], m[9], r_bl, p_bl, y_bl;
+  iso_mul(os.odom, os.l2b, bl);                  // odom_ * laser_to_base_
+  quat_from_matrix(bl, q);                        // Eigen::Quaterniond(odom_bl.rotation())
+  tf_matrix_from_quat(q, m);
+  tf_get_rpy(m, &r_bl, &p_bl, &y_bl);
+  tf_set_rpy(r_imu, p_imu, y_bl, m);
+  tf_get_rotation(m, q);
+  {  // Eigen::Quaterniond::toRotationMatrix into odom_bl.linear()
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    bl[0] = 1.0 - (tyy + tzz); bl[1] = txy - twz; bl[2] = txz + twy;
+    bl[4] = txy + twz; bl[5] = 1.0 - (txx + tzz); bl[6] = tyz - twx;
+    bl[8] = txz - twy; bl[9] = tyz + twx; bl[10] = 1.0 - (txx + tyy);
+  }
+  double inv[12], out[12];
+  iso_inverse(os.l2b, inv);
+  iso_mul(bl, inv, out);                          // odom_bl * laser_to_base_.inverse()
+  for (int k = 0; k < 12; ++k) os.odom[k] = out[k];
+}
+
 __global__ void k_predict(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.x;
   if (threadIdx.x != 0) return;
@@ -179,6 +251,7 @@ __global__ void k_predict(DevBuffers d, int lane0) {
     iso_mul(inv, os.odom, rel);
     iso_mul(os.odom, rel, pred);
     for (int k = 0; k < 12; ++k) { os.prev[k] = os.odom[k]; os.odom[k] = pred[k]; }
+    if (d.p.use_imu) imu_override(os);
     quat_from_matrix(os.odom, os.q);
     os.t[0] = os.odom[3]; os.t[1] = os.odom[7]; os.t[2] = os.odom[11];
   }

@@ -163,7 +163,7 @@ static std::shared_ptr<liodom_ctx> make_ctx(const Params* params, int max_points
   p.min_range = params->min_range_; p.max_range = params->max_range_; p.lidar_type = params->lidar_type_;
   p.scan_lines = params->scan_lines_; p.scan_regions = params->scan_regions_; p.edges_per_region = params->edges_per_region_;
   p.prev_frames = prev_frames; p.filter_local_map = params->filter_local_map_ ? 1 : 0; p.mapping = params->mapping_ ? 1 : 0;
-  p.max_points = max_points; p.max_received_map = max_received;
+  p.max_points = max_points; p.max_received_map = max_received; p.use_imu = params->use_imu_ ? 1 : 0;
   int device = 0;
   if (const char* d = std::getenv("LIODOM_DEVICE")) device = std::atoi(d);
   liodom_ctx* c = nullptr;
@@ -339,12 +339,14 @@ LaserOdometer::LaserOdometer(const NodeHandle& nh)
     : nh_(nh), init_(false), odom_(Isometry3d::Identity()), sdata(SharedData::getInstance()), stats(Stats::getInstance()),
       params(Params::getInstance()) {}
 LaserOdometer::LaserOdometer(const LaserOdometer& o)
-    : nh_(o.nh_), init_(o.init_), odom_(o.odom_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), odom_cb_(o.odom_cb_) {}
+    : nh_(o.nh_), init_(o.init_), odom_(o.odom_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), odom_cb_(o.odom_cb_),
+      odom_msg_cb_(o.odom_msg_cb_), prev_odom_(o.prev_odom_), laser_to_base_(o.laser_to_base_), prev_stamp_(o.prev_stamp_) {}
 LaserOdometer::~LaserOdometer() {}
 
 bool LaserOdometer::ensureContext() {
   if (ctx_) return true;
   ctx_ = make_ctx(params, 2048, (int)params->local_map_size_, params->mapping_ ? (1 << 20) : 0);
+  if (ctx_) liodom_odom_set_laser_to_base(ctx_.get(), 0, laser_to_base_.matrix().m);
   return (bool)ctx_;
 }
 
@@ -358,17 +360,99 @@ bool LaserOdometer::process(const PointCloud::Ptr& feats, const Header& header, 
     const int rc = liodom_set_received_map(ctx_.get(), 0, buf.data(), (int)rec->size());
     if (rc != LIODOM_OK) LIODOM_ERROR("liodom_set_received_map failed (%d): %s", rc, liodom_last_error(ctx_.get()));
   }
+  if (params->use_imu_) {   // sdata->getLastIMUOri (src/laser_odometry.cc:155-157): the override itself runs on the device
+    Quaterniond imu_ori;
+    sdata->getLastIMUOri(imu_ori);
+    const double q[4] = {imu_ori.x(), imu_ori.y(), imu_ori.z(), imu_ori.w()};
+    const int rc = liodom_odom_set_imu(ctx_.get(), 0, q);
+    if (rc != LIODOM_OK) LIODOM_ERROR("liodom_odom_set_imu failed (%d): %s", rc, liodom_last_error(ctx_.get()));
+  }
   std::vector<float> buf;
   xyzi_from_cloud(*feats, &buf);
   double pose16[16];
   liodom_frame_diag diag;
   const int rc = liodom_register(ctx_.get(), 0, buf.data(), (int)feats->size(), pose16, &diag);
   if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_register failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
+  if (init_) prev_odom_ = odom_;   // prev_odom_ = odom_ before the prediction (src/laser_odometry.cc:149)
   std::memcpy(odom_.matrix().m, pose16, sizeof(pose16));
   init_ = true;
   LIODOM_INFO("frame %u: %d edges, map %d, matches %d/%d", header.seq, diag.n_edges, diag.n_map[0], diag.n_matches[0], diag.n_matches[1]);
   if (pose_out) *pose_out = odom_;
   return true;
+}
+
+void LaserOdometer::setLaserToBase(const Isometry3d& laser_to_base) {
+  laser_to_base_ = laser_to_base;
+  if (ensureContext()) {
+    const int rc = liodom_odom_set_laser_to_base(ctx_.get(), 0, laser_to_base.matrix().m);
+    if (rc != LIODOM_OK) LIODOM_ERROR("liodom_odom_set_laser_to_base failed (%d): %s", rc, liodom_last_error(ctx_.get()));
+  }
+}
+
+// Eigen::Quaterniond(Matrix3d): trace / largest-diagonal branches
+static Quaterniond quat_from_rotation(const Isometry3d& T) {
+  Quaterniond q;
+  const double tr = T(0, 0) + T(1, 1) + T(2, 2);
+  double v[4];
+  if (tr > 0.0) {
+    double t = std::sqrt(tr + 1.0);
+    v[3] = 0.5 * t; t = 0.5 / t;
+    v[0] = (T(2, 1) - T(1, 2)) * t; v[1] = (T(0, 2) - T(2, 0)) * t; v[2] = (T(1, 0) - T(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (T(1, 1) > T(0, 0)) i = 1;
+    if (T(2, 2) > T(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(T(i, i) - T(j, j) - T(k, k) + 1.0);
+    v[i] = 0.5 * t; t = 0.5 / t;
+    v[3] = (T(k, j) - T(j, k)) * t; v[j] = (T(j, i) + T(i, j)) * t; v[k] = (T(k, i) + T(i, k)) * t;
+  }
+  q.qx = v[0]; q.qy = v[1]; q.qz = v[2]; q.qw = v[3];
+  return q;
+}
+
+// tf::Matrix3x3(tf::Quaternion).getRPY (getEulerYPR, solution 1)
+static void rpy_from_quat(const Quaterniond& q, double* roll, double* pitch, double* yaw) {
+  const double d = q.x() * q.x() + q.y() * q.y() + q.z() * q.z() + q.w() * q.w();
+  const double s = 2.0 / d;
+  const double xs = q.x() * s, ys = q.y() * s, zs = q.z() * s;
+  const double wx = q.w() * xs, wy = q.w() * ys, wz = q.w() * zs;
+  const double xx = q.x() * xs, xy = q.x() * ys, xz = q.x() * zs, yy = q.y() * ys, yz = q.y() * zs, zz = q.z() * zs;
+  const double m00 = 1.0 - (yy + zz), m01 = xy - wz, m02 = xz + wy, m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+  const double kPi = 3.14159265358979323846;
+  if (std::fabs(m20) >= 1.0) {
+    *yaw = 0.0;
+    if (m20 < 0.0) { *pitch = kPi / 2.0; *roll = std::atan2(m01, m02); }
+    else { *pitch = -kPi / 2.0; *roll = std::atan2(-m01, -m02); }
+  } else {
+    *pitch = -std::asin(m20);
+    const double cp = std::cos(*pitch);
+    *roll = std::atan2(m21 / cp, m22 / cp);
+    *yaw = std::atan2(m10 / cp, m00 / cp);
+  }
+}
+
+Odometry LaserOdometer::makeOdometry(const Header& header, const Isometry3d& pose, const Isometry3d& prev_odom,
+                                     const Isometry3d& laser_to_base, double prev_stamp, const std::string& fixed_frame,
+                                     const std::string& base_frame) {
+  Odometry msg;
+  msg.header.frame_id = fixed_frame; msg.header.stamp = header.stamp; msg.header.seq = header.seq;
+  msg.child_frame_id = base_frame;
+  const Isometry3d odom_base_link = pose * laser_to_base;   // transform to base_link before publication
+  msg.orientation = quat_from_rotation(odom_base_link);
+  for (int k = 0; k < 3; ++k) msg.position[k] = odom_base_link(k, 3);
+  const double delta_time = header.stamp.toSec() - prev_stamp;
+  const Isometry3d delta_odom = (prev_odom * laser_to_base).inverse() * odom_base_link;
+  for (int k = 0; k < 3; ++k) msg.twist_linear[k] = delta_odom(k, 3) / delta_time;
+  double roll, pitch, yaw;
+  rpy_from_quat(quat_from_rotation(delta_odom), &roll, &pitch, &yaw);
+  msg.twist_angular[0] = roll / delta_time; msg.twist_angular[1] = pitch / delta_time; msg.twist_angular[2] = yaw / delta_time;
+  return msg;
+}
+
+void LaserOdometer::publishOdom(const Header& header, const Isometry3d& pose) {
+  if (odom_msg_cb_) odom_msg_cb_(makeOdometry(header, pose, prev_odom_, laser_to_base_, prev_stamp_, params->fixed_frame_, params->base_frame_));
+  prev_stamp_ = header.stamp.toSec();   // src/laser_odometry.cc:127,264
 }
 
 void LaserOdometer::operator()(std::atomic<bool>& running) {
@@ -386,6 +470,7 @@ void LaserOdometer::operator()(std::atomic<bool>& running) {
         stats->stopFrame(end_t);
         stats->addPose(odom_.matrix());
         if (odom_cb_) odom_cb_(feat_header, odom_);
+        publishOdom(feat_header, odom_);
       }
     }
     std::this_thread::sleep_for(std::chrono::milliseconds(2));
@@ -532,6 +617,19 @@ int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans,
     pc->height = opt->lidar_type == 1 ? (uint32_t)opt->height : 1;
     return pc;
   }, poses_out, nfeats_out, results_dir);
+}
+
+// publishOdom's arithmetic through the façade (test hook): out13 = orientation x,y,z,w, position,
+// twist linear, twist angular.
+void liodom_host_make_odometry(const double* pose16, const double* prev_odom16, const double* l2b16, double stamp, double prev_stamp, double* out13) {
+  using namespace liodom;
+  Isometry3d pose, prev, l2b;
+  std::memcpy(pose.matrix().m, pose16, sizeof(double) * 16); std::memcpy(prev.matrix().m, prev_odom16, sizeof(double) * 16);
+  std::memcpy(l2b.matrix().m, l2b16, sizeof(double) * 16);
+  Header h; h.stamp.secs = stamp;
+  const Odometry m = LaserOdometer::makeOdometry(h, pose, prev, l2b, prev_stamp, "odom", "base_link");
+  out13[0] = m.orientation.x(); out13[1] = m.orientation.y(); out13[2] = m.orientation.z(); out13[3] = m.orientation.w();
+  for (int k = 0; k < 3; ++k) { out13[4 + k] = m.position[k]; out13[7 + k] = m.twist_linear[k]; out13[10 + k] = m.twist_angular[k]; }
 }
 
 // The same with sensor_msgs/PointCloud2 messages, as lidarClb receives them: `data` holds the frames'

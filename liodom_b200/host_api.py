@@ -67,3 +67,14 @@ def run_sequence_msgs(blobs, widths, heights, point_step, fields, row_pad=0, res
                                                  point_step, row_pad, names, offs.ctypes.data_as(vp), dts.ctypes.data_as(vp), len(fields),
                                                  poses.ctypes.data_as(vp), nf.ctypes.data_as(vp), results_dir.encode())
     return poses.reshape(-1, 4, 4), nf, produced
+
+
+def make_odometry(pose, prev_odom, laser_to_base, stamp, prev_stamp):
+    """LaserOdometer::publishOdom's arithmetic through the façade -> 13 doubles (orientation x,y,z,w,
+    position, twist linear, twist angular)."""
+    lib = load()
+    lib.liodom_host_make_odometry.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    a = [np.ascontiguousarray(m, dtype=np.float64) for m in (pose, prev_odom, laser_to_base)]
+    out = np.empty(13)
+    lib.liodom_host_make_odometry(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, float(stamp), float(prev_stamp), out.ctypes.data)
+    return out

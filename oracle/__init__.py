@@ -212,6 +212,11 @@ class Odometer:
         assert fs.sum() == len(pts)
         lib().orc_odom_set_window(self.h, _p(pts), _p(fs), len(fs))
 
+    def set_imu(self, use_imu, q_xyzw=None, laser_to_base=None):
+        q = None if q_xyzw is None else np.ascontiguousarray(q_xyzw, dtype=np.float64)
+        T = None if laser_to_base is None else np.ascontiguousarray(laser_to_base, dtype=np.float64)
+        lib().orc_odom_set_imu(self.h, int(use_imu), _p(q), _p(T))
+
     def set_received_map(self, pts):
         pts = _f4(pts)
         lib().orc_odom_set_received_map(self.h, _p(pts), len(pts))
@@ -245,6 +250,31 @@ def decode_cloud2(data, width, height, point_step, row_step, off_x, off_y, off_z
     data = np.ascontiguousarray(data, dtype=np.uint8)
     out = np.empty((width * height, 4), np.float32)
     lib().orc_decode_cloud2(_p(data), width, height, point_step, row_step, off_x, off_y, off_z, off_i, _p(out))
+    return out
+
+
+def tf_rpy(q_xyzw):
+    """-> (rpy [3], quaternion rebuilt from them) through tf::Matrix3x3 getRPY / setRPY / getRotation."""
+    q = np.ascontiguousarray(q_xyzw, dtype=np.float64)
+    rpy = np.empty(3)
+    back = np.empty(4)
+    lib().orc_tf_rpy(_p(q), _p(rpy), _p(back))
+    return rpy, back
+
+
+def imu_override(odom, imu_q_xyzw, laser_to_base):
+    out = np.empty((4, 4))
+    lib().orc_imu_override(_p(np.ascontiguousarray(odom, dtype=np.float64)), _p(np.ascontiguousarray(imu_q_xyzw, dtype=np.float64)),
+                           _p(np.ascontiguousarray(laser_to_base, dtype=np.float64)), _p(out))
+    return out
+
+
+def publish_odom(pose, prev_odom, laser_to_base, delta_time):
+    """-> 13 doubles: orientation x,y,z,w, position, twist linear, twist angular (publishOdom)."""
+    out = np.empty(13)
+    lib().orc_publish_odom.argtypes = [_vp, _vp, _vp, ctypes.c_double, _vp]
+    lib().orc_publish_odom(_p(np.ascontiguousarray(pose, dtype=np.float64)), _p(np.ascontiguousarray(prev_odom, dtype=np.float64)),
+                           _p(np.ascontiguousarray(laser_to_base, dtype=np.float64)), float(delta_time), _p(out))
     return out
 
 

@@ -755,6 +755,75 @@ inline void matrix_from_quat(const double* q, Iso& A) {
 }
 
 // ---------------------------------------------------------------------------------
+// tf (bullet LinearMath) pieces used by the IMU override and publishOdom
+// (src/laser_odometry.cc:152-183, :395-446): Matrix3x3(Quaternion) = setRotation, getRPY =
+// getEulerYPR solution 1, setRPY = setEulerYPR, getRotation.  Third-party (ros/geometry tf,
+// Noetic 1.13), source not in /root/reference: restated from the published header; parity unpinned.
+// Matrices row-major 3x3; quaternions (x,y,z,w).
+// ---------------------------------------------------------------------------------
+inline void tf_matrix_from_quat(const double* q, double* m) {
+  const double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const double s = 2.0 / d;
+  const double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+  const double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+  const double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs, yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+  m[0] = 1.0 - (yy + zz); m[1] = xy - wz; m[2] = xz + wy;
+  m[3] = xy + wz; m[4] = 1.0 - (xx + zz); m[5] = yz - wx;
+  m[6] = xz - wy; m[7] = yz + wx; m[8] = 1.0 - (xx + yy);
+}
+inline void tf_get_rpy(const double* m, double* roll, double* pitch, double* yaw) {
+  const double kPi = 3.14159265358979323846;
+  if (std::fabs(m[6]) >= 1.0) {
+    *yaw = 0.0;
+    if (m[6] < 0.0) { *pitch = kPi / 2.0; *roll = std::atan2(m[1], m[2]); }
+    else { *pitch = -kPi / 2.0; *roll = std::atan2(-m[1], -m[2]); }
+  } else {
+    *pitch = -std::asin(m[6]);
+    const double cp = std::cos(*pitch);
+    *roll = std::atan2(m[7] / cp, m[8] / cp);
+    *yaw = std::atan2(m[3] / cp, m[0] / cp);
+  }
+}
+inline void tf_set_rpy(double roll, double pitch, double yaw, double* m) {
+  const double ci = std::cos(roll), cj = std::cos(pitch), ch = std::cos(yaw), si = std::sin(roll), sj = std::sin(pitch), sh = std::sin(yaw);
+  const double cc = ci * ch, cs = ci * sh, sc = si * ch, ss = si * sh;
+  m[0] = cj * ch; m[1] = sj * sc - cs; m[2] = sj * cc + ss;
+  m[3] = cj * sh; m[4] = sj * ss + cc; m[5] = sj * cs - sc;
+  m[6] = -sj; m[7] = cj * si; m[8] = cj * ci;
+}
+inline void tf_get_rotation(const double* m, double* q) {
+  const double trace = m[0] + m[4] + m[8];
+  if (trace > 0.0) {
+    double s = std::sqrt(trace + 1.0);
+    q[3] = s * 0.5; s = 0.5 / s;
+    q[0] = (m[7] - m[5]) * s; q[1] = (m[2] - m[6]) * s; q[2] = (m[3] - m[1]) * s;
+  } else {
+    const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = std::sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+    q[i] = s * 0.5; s = 0.5 / s;
+    q[3] = (m[k * 3 + j] - m[j * 3 + k]) * s; q[j] = (m[j * 3 + i] + m[i * 3 + j]) * s; q[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+  }
+}
+// src/laser_odometry.cc:152-183
+inline Iso imu_override(const Iso& odom, const double* imu_q, const Iso& l2b) {
+  double imu_m[9], r_imu, p_imu, y_imu;
+  tf_matrix_from_quat(imu_q, imu_m);
+  tf_get_rpy(imu_m, &r_imu, &p_imu, &y_imu);
+  Iso bl = iso_mul(odom, l2b);
+  double q[4], m[9], r_bl, p_bl, y_bl;
+  quat_from_matrix(bl, q);
+  tf_matrix_from_quat(q, m);
+  tf_get_rpy(m, &r_bl, &p_bl, &y_bl);
+  tf_set_rpy(r_imu, p_imu, y_bl, m);
+  tf_get_rotation(m, q);
+  Iso R = iso_identity();
+  matrix_from_quat(q, R);
+  for (int i = 0; i < 3; ++i) for (int jj = 0; jj < 3; ++jj) bl.m[i * 4 + jj] = R.m[i * 4 + jj];
+  return iso_mul(bl, iso_inverse(l2b));
+}
+
+// ---------------------------------------------------------------------------------
 // A.3 pcl::VoxelGrid<PointXYZI>::applyFilter (PCL 1.10 voxel_grid.hpp), cubic leaf,
 // downsample_all_data = true, min_points_per_voxel = 0, no filter field.
 // ---------------------------------------------------------------------------------
@@ -828,6 +897,9 @@ struct OrcOdom {
   bool init = false;
   Iso prev_odom = iso_identity(), odom = iso_identity();
   double param_q[4] = {0, 0, 0, 1}, param_t[3] = {0, 0, 0};
+  bool use_imu = false;                       // params->use_imu_
+  double imu_q[4] = {0, 0, 0, 1};             // SharedData::getLastIMUOri
+  Iso laser_to_base = iso_identity();         // getBaseToLaserTf
   OrcLmap lmap;
   std::vector<P4> received;  // SharedData::local_map_
 };
@@ -1031,6 +1103,43 @@ void orc_odom_set_window(OrcOdom* o, const float* xyzi, const int32_t* frame_siz
   o->lmap.total_points.assign(reinterpret_cast<const P4*>(xyzi), reinterpret_cast<const P4*>(xyzi) + tot);
   o->lmap.sizes = q; o->lmap.nframes = (size_t)nframes; o->init = nframes > 0;
 }
+void orc_odom_set_imu(OrcOdom* o, int use_imu, const double* q_xyzw, const double* laser_to_base16) {
+  o->use_imu = use_imu != 0;
+  if (q_xyzw) std::memcpy(o->imu_q, q_xyzw, sizeof(o->imu_q));
+  if (laser_to_base16) std::memcpy(o->laser_to_base.m, laser_to_base16, sizeof(o->laser_to_base.m));
+}
+
+void orc_tf_rpy(const double* q_xyzw, double* rpy3, double* q_back_xyzw) {
+  double m[9], m2[9];
+  tf_matrix_from_quat(q_xyzw, m);
+  tf_get_rpy(m, rpy3, rpy3 + 1, rpy3 + 2);
+  tf_set_rpy(rpy3[0], rpy3[1], rpy3[2], m2);
+  tf_get_rotation(m2, q_back_xyzw);
+}
+
+void orc_imu_override(const double* odom16, const double* imu_q_xyzw, const double* l2b16, double* out16) {
+  Iso o, l; std::memcpy(o.m, odom16, sizeof(o.m)); std::memcpy(l.m, l2b16, sizeof(l.m));
+  Iso r = imu_override(o, imu_q_xyzw, l);
+  std::memcpy(out16, r.m, sizeof(r.m));
+}
+
+// publishOdom (src/laser_odometry.cc:395-446): out[13] = orientation x,y,z,w, position x,y,z,
+// twist linear x,y,z, twist angular x,y,z.  prev_odom16 = prev_odom_ at the time of the call.
+void orc_publish_odom(const double* pose16, const double* prev_odom16, const double* l2b16, double delta_time, double* out13) {
+  Iso pose, prev, l2b;
+  std::memcpy(pose.m, pose16, sizeof(pose.m)); std::memcpy(prev.m, prev_odom16, sizeof(prev.m)); std::memcpy(l2b.m, l2b16, sizeof(l2b.m));
+  const Iso obl = iso_mul(pose, l2b);
+  quat_from_matrix(obl, out13);
+  out13[4] = obl.m[3]; out13[5] = obl.m[7]; out13[6] = obl.m[11];
+  const Iso delta = iso_mul(iso_inverse(iso_mul(prev, l2b)), obl);
+  out13[7] = delta.m[3] / delta_time; out13[8] = delta.m[7] / delta_time; out13[9] = delta.m[11] / delta_time;
+  double qd[4], m[9], r, p, y;
+  quat_from_matrix(delta, qd);
+  tf_matrix_from_quat(qd, m);
+  tf_get_rpy(m, &r, &p, &y);
+  out13[10] = r / delta_time; out13[11] = p / delta_time; out13[12] = y / delta_time;
+}
+
 void orc_odom_set_received_map(OrcOdom* o, const float* xyzi, int n) {
   o->received.assign(reinterpret_cast<const P4*>(xyzi), reinterpret_cast<const P4*>(xyzi) + n);
 }
@@ -1059,6 +1168,7 @@ void orc_odom_process(OrcOdom* o, const float* edges_xyzi, int E, double* pose_o
     Iso pred = iso_mul(o->odom, iso_mul(iso_inverse(o->prev_odom), o->odom));
     o->prev_odom = o->odom;
     o->odom = pred;
+    if (o->use_imu) o->odom = imu_override(o->odom, o->imu_q, o->laser_to_base);   // :152-183
     std::memcpy(D.pred_pose, o->odom.m, sizeof(D.pred_pose));
     // initial guess (:186-195)
     quat_from_matrix(o->odom, o->param_q);

@@ -121,6 +121,14 @@ int orc_odom_window_frames(const OrcOdom* o);
 void orc_odom_get_window(const OrcOdom* o, float* xyzi);
 void orc_odom_set_window(OrcOdom* o, const float* xyzi, const int32_t* frame_sizes, int nframes);
 void orc_odom_set_received_map(OrcOdom* o, const float* xyzi, int n);  /* SharedData::setLocalMap */
+/* use_imu (src/laser_odometry.cc:152-183): roll/pitch of the predicted pose, expressed in base_link
+ * through laser_to_base (row-major 4x4), replaced by the IMU orientation's. */
+void orc_odom_set_imu(OrcOdom* o, int use_imu, const double* q_xyzw, const double* laser_to_base16);
+/* tf round trip used by both: rpy3 = getRPY(Matrix3x3(q)), q_back = getRotation(setRPY(rpy3)). */
+void orc_tf_rpy(const double* q_xyzw, double* rpy3, double* q_back_xyzw);
+void orc_imu_override(const double* odom16, const double* imu_q_xyzw, const double* l2b16, double* out16);
+/* publishOdom (src/laser_odometry.cc:395-446): out13 = orientation (x,y,z,w), position, twist linear, twist angular. */
+void orc_publish_odom(const double* pose16, const double* prev_odom16, const double* l2b16, double delta_time, double* out13);
 typedef struct {
   int n_edges;
   int n_map[2];
