@@ -491,11 +491,28 @@ __device__ __forceinline__ void knn_scan_row(const HashEntry* __restrict__ tab, 
 
 constexpr int kAssocThreads = 64;
 
+// Visit order of the 27 cells of a cube: per axis 0 = own cell, 1 = the neighbour behind the nearer
+// face, 2 = the one behind the farther face; sorted by sum of weights (0, 1, 4).  Entry = ax | ay << 2 | az << 4.
+__constant__ unsigned char kNearOrder[27] = {
+    0x00,                                     // (0,0,0)
+    0x01, 0x04, 0x10,                         // one near
+    0x05, 0x11, 0x14,                         // two near
+    0x15,                                     // three near
+    0x02, 0x08, 0x20,                         // one far
+    0x06, 0x09, 0x12, 0x18, 0x21, 0x24,       // one far + one near
+    0x16, 0x19, 0x25,                         // one far + two near
+    0x0a, 0x22, 0x28,                         // two far
+    0x1a, 0x26, 0x29,                         // two far + one near
+    0x2a};                                    // three far
+
 // G threads per edge (G = 1 for large batches: least work; G = 4 when few edges are in flight:
 // shorter critical path): transform (A.1: double math, float store), exact 5-NN, line gate
 // (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
 template <int G>
-__global__ void __launch_bounds__(kAssocThreads, G == 1 ? 20 : 8) k_associate(DevBuffers d, int lane0, int outer_it, int force,
+#ifndef LIODOM_ASSOC_MINB
+#define LIODOM_ASSOC_MINB 20
+#endif
+__global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8) k_associate(DevBuffers d, int lane0, int outer_it, int force,
                                                                               const double* pose_override, int shard_rank, int shard_world) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y;
@@ -532,10 +549,28 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? 20 : 8) k_associate(De
     // warp-per-edge variant with the buckets concatenated across the lanes were measured slower.)
     if (G == 1) {
       if (searchable) {
+        // the 9 occupancy words of the cube are requested together with the own cell's probe (10 loads in
+        // flight, one round trip) instead of one dependent load per row
+        unsigned occ = 0;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) occ |= bloom_row(bloom, bmask, cx - 1, 3, cy + r % 3 - 1, cz + r / 3 - 1) << (3 * r);
         const uint2 sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
         knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, 3.0e38f, k);
-        for (int r = 0; r < 9; ++r)
-          knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, cx - 1, 3, r == 4 ? 2u : 0u, cy + r % 3 - 1, cz + r / 3 - 1, qx, qy, qz, 3.0e38f, k);
+        occ &= ~(1u << 13);
+        // neighbours nearest first (per axis: own, then the side of the nearer face, then the far side), so
+        // that the bound tightens before the far cells are looked at and most of them fall to cell_min_d2
+        const int nx = __fsub_rn(qx, kCell * (float)cx) < 0.5f * kCell ? -1 : 1;
+        const int ny = __fsub_rn(qy, kCell * (float)cy) < 0.5f * kCell ? -1 : 1;
+        const int nz = __fsub_rn(qz, kCell * (float)cz) < 0.5f * kCell ? -1 : 1;
+        for (int i = 1; i < 27 && occ; ++i) {
+          const unsigned code = kNearOrder[i];
+          const int ax = code & 3, ay = (code >> 2) & 3, az = code >> 4;
+          const int dx = ax == 0 ? 0 : (ax == 1 ? nx : -nx), dy = ay == 0 ? 0 : (ay == 1 ? ny : -ny), dz = az == 0 ? 0 : (az == 1 ? nz : -nz);
+          const unsigned bit = 1u << (((dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1));
+          if (!(occ & bit)) continue;
+          occ &= ~bit;
+          knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
+        }
       }
     } else {
       // the group strides over the own cell together, shares the tightest 5th-best as a bound, splits

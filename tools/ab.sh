@@ -3,4 +3,4 @@
 extra="$1"; envs="$2"; shift 2
 LIODOM_NVCC_EXTRA="$extra" python -c "from liodom_b200 import build; build.build(force=True)" >/dev/null 2>&1 || echo BUILD FAILED
 echo "== flags[$extra] env[$envs] args[$*]"
-env $envs python bench.py --no-cpu-baseline "$@" | python tools/benchline.py
+env $envs timeout 120 python bench.py --no-cpu-baseline "$@" | python tools/benchline.py
