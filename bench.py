@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LIODOM_BENCH_LANES", "32")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LIODOM_BENCH_LANES", "128")),
                     help="independent sequences per GPU processed by one step")
     ap.add_argument("--sensor", default="hdl64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -135,8 +135,9 @@ def run_b200(args):
     max_points = 131072 if args.sensor == "hdl64" else 1 << 20
     kw = dict(prev_frames=15, max_points=max_points)   # launch/liodom.launch:17-31
 
-    # inputs resident in HBM: one tensor per (sequence, frame)
-    dev_scans = [[torch.from_numpy(seqs[s][f]).to(dev) for f in range(nframes)] for s in range(nseq)]
+    # inputs resident in HBM: one tensor per (lane, frame).  Lanes that replay the same synthetic sequence
+    # still get their own copy, so that no lane finds its scan in L2 because another lane just read it.
+    dev_scans = [[torch.from_numpy(seqs[l % nseq][f]).to(dev) for f in range(nframes)] for l in range(B)]
     # pinned host buffers for the end-to-end leg: the B scans of a step back to back (what a batching
     # front-end hands over), so that the library can move a step over PCIe as one copy
     host_steps, host_ptrs = [], []
@@ -164,7 +165,7 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def step_dev(f):
-        ptrs = [dev_scans[l % nseq][f].data_ptr() for l in range(B)]
+        ptrs = [dev_scans[l][f].data_ptr() for l in range(B)]
         cnts = [int(npts[l % nseq][f]) for l in range(B)]
         ctx.scan_batch_ptrs(ptrs, cnts, BYTES_PER_POINT, on_device=True)
 
@@ -285,6 +286,18 @@ def run_b200(args):
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
+    # what the PCIe link alone would allow: the same pinned step buffers copied back to back, nothing else running
+    nprobe = min(K, 8)
+    probe = torch.empty((max(len(host_steps[f]) for f in range(W, W + nprobe)), 4), dtype=torch.float32, device=dev)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pe0.record()
+    for f in range(W, W + nprobe):
+        probe[:len(host_steps[f])].copy_(host_steps[f], non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_alone_gbps = sum(host_steps[f].numel() * 4 for f in range(W, W + nprobe)) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    h2d_in_run_gbps = h2d / (e2e_ms * 1e-3) / 1e9
     # the two legs must agree on the answer: same scans, same start state
     same = bool(np.array_equal(poses_e2e, poses_dev))
     ctx.close()
@@ -307,11 +320,13 @@ def run_b200(args):
                                "(scan_regions=8, edges_per_region=10, prev_frames=15, range 3-75 m), extract+register",
                    "lanes_per_gpu": B, "distinct_sequences_per_gpu": nseq, "points_per_scan": int(npts.mean()),
                    "sharding": "independent sequences per GPU, no collective",
-                   "l2": "every step reads a distinct scan batch (%d MB/step/GPU; %d MB over the run > 126 MB L2), uploaded before timing"
-                         % (int(B * npts.mean() * 16 / 1e6), int(nseq * npts.sum(axis=1).mean() * 16 / 1e6))},
+                   "l2": "every step reads a distinct scan batch at distinct addresses per lane (%d MB/step/GPU; %d MB over the run; L2 is 126 MB), uploaded before timing"
+                         % (int(B * npts.mean() * 16 / 1e6), int(B * npts.sum(axis=1).mean() * 16 / 1e6))},
         "ms_per_scan": round(ms_total / K / B, 5),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
-                "ms_per_step": round(e2e_ms / K, 4), "same_poses_as_device_leg": same},
+                "ms_per_step": round(e2e_ms / K, 4), "same_poses_as_device_leg": same,
+                "h2d_gbps_in_run": round(h2d_in_run_gbps, 1), "h2d_gbps_link_alone": round(h2d_alone_gbps, 1),
+                "bound": "PCIe H2D of the raw scans (16 B/point)" if h2d_in_run_gbps > 0.85 * h2d_alone_gbps else "kernels"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "synth_seconds": round(gen_s, 1),

@@ -5,6 +5,7 @@
 // Bit-exact parts (transform, float L2 distances, centroid/scatter/eigen gate) use the
 // explicit *_rn intrinsics and the file is compiled with -fmad=false.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace liodom {
@@ -114,17 +115,24 @@ __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
   }
 }
 
+// Clears the occupancy filters of the lanes (a kernel, not cudaMemsetAsync: a memset may be placed on a
+// copy engine, where it would wait behind the next scan's H2D transfer).
+__global__ void __launch_bounds__(256) k_bloom_clear(DevBuffers d, int lane0) {
+  uint4* w = reinterpret_cast<uint4*>(d.bloom + (size_t)(lane0 + blockIdx.y) * d.p.Bwords);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.p.Bwords / 4; i += gridDim.x * blockDim.x) w[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   const int lane0 = lr.lane0, nlanes = lr.nlanes;
   int blocks = (d.p.Mcap + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   const dim3 g(blocks, nlanes);
   const int nf = launch_window_filter(d, s, lr);
-  cudaMemsetAsync(d.bloom + (size_t)lane0 * d.p.Bwords, 0, sizeof(unsigned) * (size_t)d.p.Bwords * nlanes, s);
+  k_bloom_clear<<<dim3(std::max(1, std::min(d.p.Bwords / 4 / 256, 64)), nlanes), 256, 0, s>>>(d, lane0);
   k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
   k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
   k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
-  return 3 + nf;
+  return 4 + nf;
 }
 
 // ---------------------------------------------------------------------------------------
