@@ -336,7 +336,7 @@ def run_b200(args):
         out["stages"] = stages
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    emit(out)
 
 
 def cpu_baseline_single_stream(seqs, budget_s):
@@ -407,11 +407,30 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, written to the process's original stdout."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line.encode())
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Libraries print to stdout on their own (NCCL's version banner under torchrun): keep fd 1 for the
+    # JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
