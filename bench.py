@@ -115,12 +115,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and hence first-touch its pinned staging buffers) on the CPUs next to its GPU, so that
+    the H2D transfers of the ranks of a node do not all cross the same socket link."""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return "%s cpus %s" % (bdf, cpus)
+    except Exception as e:   # best effort: containers may hide sysfs or the affinity call
+        return "unbound (%s)" % e
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from liodom_b200 import api
 
     rank, world, local = dist_env()
+    numa = bind_to_gpu_numa_node(local)
+    sys.stderr.write("[bench] rank %d: %s\n" % (rank, numa))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
