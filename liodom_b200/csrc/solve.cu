@@ -264,8 +264,10 @@ __device__ void lm_init(LmCtrl& c, const OdomState& os) {
 // (next point + action) is read back by the other CTAs through DSMEM.
 // F32: residual blocks come from k_associate (float records {c,a,b,valid}); otherwise from a
 // caller-provided double array (liodom_solve, tests).
-template <bool F32>
-__global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0, int outer_it, const double* cab_in, int n_in,
+// OCC = CTAs per SM the register budget is compiled for: 1 (≈200 registers, no spills: lowest latency, used for
+// small batches) or 2 (128 registers with spills: two clusters' worth of warps per SM, 20 % faster at 128 lanes).
+template <bool F32, int OCC>
+__global__ void __launch_bounds__(kSolveThreads, OCC) k_solve(DevBuffers d, int lane0, int outer_it, const double* cab_in, int n_in,
                                                           double* qt_inout, SolveSummaryDev* sum_out) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -342,18 +344,19 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(DevBuffers d, int lane0
   cluster.sync();   // nobody leaves while its shared memory may still be read
 }
 
-// Cluster size: as many CTAs per lane as keep the whole grid in one wave (the kernel needs ~200
-// registers per thread, so one 256-thread CTA per SM; 148 SMs).
-static int solve_cluster_size(int nlanes) {
+// Cluster size: as many CTAs per lane as keep the whole grid in one wave (148 SMs x `occ` resident
+// 256-thread CTAs per SM).
+static int solve_cluster_size(int nlanes, int occ) {
   int c = 8;
-  while (c > 1 && nlanes * c > 148) c >>= 1;
+  while (c > 1 && nlanes * c > 148 * occ) c >>= 1;
   return c;
 }
 
 template <bool F32>
 static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, int nlanes, int outer_it, const double* cab, int n,
                                 double* qt, SolveSummaryDev* sum) {
-  const int C = solve_cluster_size(nlanes);
+  const int occ = nlanes >= 16 ? 2 : 1;   // measured: the 2-per-SM build wins from 32 lanes up, loses 8 % on a single lane
+  const int C = solve_cluster_size(nlanes, occ);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(nlanes * C));
   cfg.blockDim = dim3(kSolveThreads);
@@ -363,7 +366,8 @@ static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_solve<F32>, d, lane0, outer_it, cab, n, qt, sum);
+  if (occ == 2) cudaLaunchKernelEx(&cfg, k_solve<F32, 2>, d, lane0, outer_it, cab, n, qt, sum);
+  else cudaLaunchKernelEx(&cfg, k_solve<F32, 1>, d, lane0, outer_it, cab, n, qt, sum);
 }
 
 // ---- point-sharded solve: evaluation over this rank's edges, all-reduce, replicated controller ----
