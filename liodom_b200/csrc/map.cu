@@ -21,6 +21,7 @@
 // over [old points in stored order..., new points in input order...], so the in-voxel float
 // accumulation order is exactly "old centroid first, then new points in arrival order".
 #include "../../include/liodom_b200.h"
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -107,347 +108,406 @@ __device__ __forceinline__ int find_slot(const MapDev& m, unsigned long long key
   }
 }
 
-// ---- update, step 1: transform, key, find-or-create hash slot -------------------------------
-__global__ void __launch_bounds__(256) k_map_insert(MapDev m, const float4* in, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 s = in[i];
-  float4 p;
-  p.x = xform_row(m.pose, s.x, s.y, s.z); p.y = xform_row(m.pose + 4, s.x, s.y, s.z); p.z = xform_row(m.pose + 8, s.x, s.y, s.z);
-  p.w = s.w;
-  m.newpts[i] = p;
-  m.pt_slot[i] = -1;
-  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { atomicAdd(&m.st->n_dropped, 1); return; }
-  const int kx = cell_key_axis(p.x, m.inv_xy, m.xy, m.xy_half), ky = cell_key_axis(p.y, m.inv_xy, m.xy, m.xy_half);
-  const int kz = cell_key_axis(p.z, m.inv_z, m.zs, m.z_half);
-  unsigned long long key;
-  if (!pack_key(kx, ky, kz, &key)) { atomicOr(&m.st->error, 1); return; }
-  unsigned slot = hash_key(key) & (unsigned)(m.hcap - 1);
-  for (;;) {
-    unsigned long long cur = ((volatile unsigned long long*)m.htab)[slot];
-    if (cur == kEmptyKey) {
-      cur = atomicCAS(&m.htab[slot], kEmptyKey, key);
-      if (cur == kEmptyKey) {  // created: remember it for id assignment
-        const int k = atomicAdd(&m.st->n_new_slots, 1);
-        if (k < m.cap_new) m.new_slots[k] = (int)slot; else atomicOr(&m.st->error, 2);
-        cur = key;
-      }
-    }
-    if (cur == key) break;
-    slot = (slot + 1) & (unsigned)(m.hcap - 1);
-  }
-  atomicMin(&m.hfirst[slot], i);
-  m.pt_slot[i] = (int)slot;
-}
-
-// step 2: new cells get ids in order of first appearance in the input (cells_vector_ order)
-__global__ void k_map_assign(MapDev m) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  MapState& st = *m.st;
-  const int nn = min(st.n_new_slots, m.cap_new);
-  for (int a = 1; a < nn; ++a) {  // insertion sort by first input index (a handful of cells per update)
-    const int s = m.new_slots[a], f = m.hfirst[s];
-    int b = a - 1;
-    while (b >= 0 && m.hfirst[m.new_slots[b]] > f) { m.new_slots[b + 1] = m.new_slots[b]; --b; }
-    m.new_slots[b + 1] = s;
-  }
-  const int lim = 1 << 20;
-  for (int a = 0; a < nn; ++a) {
-    const int s = m.new_slots[a];
-    if (st.num_cells >= m.cap_cells) { st.error |= 2; break; }
-    const int id = st.num_cells++;
-    m.hval[s] = id;
-    const unsigned long long k = m.htab[s];
-    m.cell_key[id * 3 + 0] = (int)((k >> 42) & 0x1fffff) - lim;
-    m.cell_key[id * 3 + 1] = (int)((k >> 21) & 0x1fffff) - lim;
-    m.cell_key[id * 3 + 2] = (int)(k & 0x1fffff) - lim;
-    m.cell_count[id] = 0;
-  }
-  st.n_new_slots = 0;
-}
-
-// step 3: point -> cell id, touched flags
-__global__ void __launch_bounds__(256) k_map_mark(MapDev m, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int s = m.pt_slot[i];
-  int cid = -1;
-  if (s >= 0) { cid = m.hval[s]; if (cid >= 0) m.touched[cid] = 1; }
-  m.pt_cell[i] = cid;
-}
-
-// step 4 (one CTA): prefix sums over the cells: old offsets, touched ranks, work offsets
-__global__ void __launch_bounds__(1024) k_map_plan(MapDev m) {
-  __shared__ int s_a[1024], s_b[1024], s_c[1024];
-  __shared__ int carry[3];
-  const int nc = m.st->num_cells, tid = threadIdx.x;
-  if (tid < 3) carry[tid] = 0;
-  __syncthreads();
-  for (int base = 0; base < nc; base += 1024) {
-    const int c = base + tid;
-    const int cnt = c < nc ? m.cell_count[c] : 0, t = c < nc ? m.touched[c] : 0;
-    s_a[tid] = cnt; s_b[tid] = t; s_c[tid] = t ? cnt : 0;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int va = tid >= o ? s_a[tid - o] : 0, vb = tid >= o ? s_b[tid - o] : 0, vc = tid >= o ? s_c[tid - o] : 0;
-      __syncthreads();
-      s_a[tid] += va; s_b[tid] += vb; s_c[tid] += vc;
-      __syncthreads();
-    }
-    if (c < nc) {
-      m.cell_off[c] = carry[0] + s_a[tid] - cnt;
-      const int r = carry[1] + s_b[tid] - t;
-      m.rank[c] = r;
-      if (t) { m.touched_list[r] = c; m.woff[r] = carry[2] + s_c[tid] - cnt; }
-    }
-    __syncthreads();
-    if (tid == 1023) { carry[0] += s_a[1023]; carry[1] += s_b[1023]; carry[2] += s_c[1023]; }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    m.cell_off[nc] = carry[0];
-    m.woff[carry[1]] = carry[2];
-    m.st->n_touched = carry[1];
-    m.st->w_old = carry[2];
-  }
-}
-
-// step 5: sort keys of the work set [old points of touched cells (rank order, stored order) | new points]
 __device__ __forceinline__ int lattice(float v, float inv_leaf) { return (int)floorf(v * inv_leaf); }
-__global__ void __launch_bounds__(256) k_map_workkeys(MapDev m, int cur, int w_old, int n_new, int n_touched) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= w_old + n_new) return;
-  float4 p; int r, cid;
-  if (w < w_old) {
-    int lo = 0, hi = n_touched;  // last rank with woff[rank] <= w
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.woff[mid] <= w) lo = mid; else hi = mid; }
-    r = lo; cid = m.touched_list[r];
-    p = m.pool[cur][m.cell_off[cid] + (w - m.woff[r])];
-  } else {
-    const int j = w - w_old;
-    cid = m.pt_cell[j];
-    p = m.newpts[j];
-    if (cid < 0) { m.keys[0][w] = kEmptyKey; m.vals[0][w] = (unsigned)w; return; }  // dropped point: sorts last
-    r = m.rank[cid];
-  }
-  // lattice relative to the cell's lower corner (with a 2-voxel margin for float rounding at the faces)
-  const float fx = (float)((double)m.cell_key[cid * 3 + 0] - m.xy_half), fy = (float)((double)m.cell_key[cid * 3 + 1] - m.xy_half);
-  const float fz = (float)((double)m.cell_key[cid * 3 + 2] - m.z_half);
-  const int lx = lattice(p.x, m.inv_leaf) - (lattice(fx, m.inv_leaf) - 2), ly = lattice(p.y, m.inv_leaf) - (lattice(fy, m.inv_leaf) - 2);
-  const int lz = lattice(p.z, m.inv_leaf) - (lattice(fz, m.inv_leaf) - 2);
-  const int lim = 1 << kLatBits;
-  if (lx < 0 || lx >= lim || ly < 0 || ly >= lim || lz < 0 || lz >= lim) atomicOr(&m.st->error, 4);
-  m.keys[0][w] = ((unsigned long long)r << kRankShift) | ((unsigned long long)(lz & (lim - 1)) << (2 * kLatBits)) |
-                 ((unsigned long long)(ly & (lim - 1)) << kLatBits) | (unsigned long long)(lx & (lim - 1));
-  m.vals[0][w] = (unsigned)w;
-}
 
-// ---- stable LSD radix sort, 8-bit digits -------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rs_hist(const unsigned long long* keys, int n, int shift, int* hist, int nblk) {
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const int base = blockIdx.x * kTile;
-  for (int k = threadIdx.x; k < kTile; k += 256) {
-    const int i = base + k;
-    if (i < n) atomicAdd(&h[(unsigned)(keys[i] >> shift) & 255u], 1);
-  }
-  __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
-}
+// ---------------------------------------------------------------------------------------------------
+// Map::updateMap as ONE cooperative launch.  An update touches a few tens of thousands of points, so
+// the ~30 dependent launches and two mid-update host round trips of a kernel-per-step pipeline cost more
+// than the work; here every step is a grid-stride phase of a single persistent grid (one 256-thread CTA
+// per SM) separated by grid-wide barriers, and the sizes that used to travel to the host (touched
+// cells, work-set size, number of voxels, radix passes) are read from device memory by every thread.
+// ---------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kMapThreads = 256;
 
-// exclusive scan of `n` ints by one CTA (n = 256 * blocks of the sort, or the head flags via 2 levels)
-__global__ void __launch_bounds__(1024) k_scan1(int* data, int n, int* total) {
-  __shared__ int s[1024];
-  __shared__ int carry;
-  const int tid = threadIdx.x;
-  if (tid == 0) carry = 0;
+// exclusive scan of data[0..n) by ONE CTA of 256 threads (8 consecutive items per thread and round)
+__device__ void block_scan_excl(int* data, int n, int* total) {
+  __shared__ int s_wtot[8];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, ln = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 4096) {
-    int v[4], sum = 0;
-    for (int k = 0; k < 4; ++k) { const int i = base + tid * 4 + k; v[k] = i < n ? data[i] : 0; sum += v[k]; }
-    s[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      const int t = tid >= o ? s[tid - o] : 0;
-      __syncthreads();
-      s[tid] += t;
-      __syncthreads();
-    }
-    int run = carry + s[tid] - sum;
-    for (int k = 0; k < 4; ++k) { const int i = base + tid * 4 + k; if (i < n) data[i] = run; run += v[k]; }
-    __syncthreads();
-    if (tid == 1023) carry += s[1023];
-    __syncthreads();
-  }
-  if (tid == 0 && total) *total = carry;
-}
-
-// two-level scan for long arrays: per-block (4096 items) sums, scan of the sums, then local scans
-__global__ void __launch_bounds__(1024) k_scan_blocksum(const int* data, int n, int* sums) {
-  __shared__ int s[32];
-  const int base = blockIdx.x * 4096, tid = threadIdx.x;
-  int sum = 0;
-  for (int k = 0; k < 4; ++k) { const int i = base + tid * 4 + k; if (i < n) sum += data[i]; }
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if ((tid & 31) == 0) s[tid >> 5] = sum;
-  __syncthreads();
-  if (tid < 32) {
-    int v = s[tid];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (tid == 0) sums[blockIdx.x] = v;
-  }
-}
-__global__ void __launch_bounds__(1024) k_scan_local(int* data, int n, const int* sums) {
-  __shared__ int s[1024];
-  const int base = blockIdx.x * 4096, tid = threadIdx.x;
-  int v[4], sum = 0;
-  for (int k = 0; k < 4; ++k) { const int i = base + tid * 4 + k; v[k] = i < n ? data[i] : 0; sum += v[k]; }
-  s[tid] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int t = tid >= o ? s[tid - o] : 0;
-    __syncthreads();
-    s[tid] += t;
-    __syncthreads();
-  }
-  int run = sums[blockIdx.x] + s[tid] - sum;
-  for (int k = 0; k < 4; ++k) { const int i = base + tid * 4 + k; if (i < n) data[i] = run; run += v[k]; }
-}
-
-// stable scatter: each warp owns a contiguous 256-key segment of the tile, processed in 8 rounds
-__global__ void __launch_bounds__(256) k_rs_scatter(const unsigned long long* kin, const unsigned* vin, unsigned long long* kout,
-                                                     unsigned* vout, int n, int shift, const int* hist, int nblk) {
-  __shared__ int wcnt[8][256];
-  for (int k = threadIdx.x; k < 8 * 256; k += 256) (&wcnt[0][0])[k] = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  const int base = blockIdx.x * kTile;
-  int dg[8];
+  for (int base = 0; base < n; base += kMapThreads * 8) {
+    int v[8], sum = 0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int i = base + w * 256 + r * 32 + ln;
-    const int d = i < n ? (int)((unsigned)(kin[i] >> shift) & 255u) : -1;
-    dg[r] = d;
-    const unsigned mm = __match_any_sync(0xffffffffu, d);
-    if (d >= 0 && (__ffs(mm) - 1) == ln) wcnt[w][d] += __popc(mm);
-    __syncwarp();
-  }
-  __syncthreads();
-  {
-    const int d = threadIdx.x;
-    int run = hist[d * nblk + blockIdx.x];
+    for (int k = 0; k < 8; ++k) { const int i = base + tid * 8 + k; v[k] = i < n ? data[i] : 0; sum += v[k]; }
+    int incl = sum;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) { const int c = wcnt[ww][d]; wcnt[ww][d] = run; run += c; }
-  }
-  __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += t; }
+    if (ln == 31) s_wtot[w] = incl;
+    __syncthreads();
+    int before = s_carry;
+    for (int k = 0; k < w; ++k) before += s_wtot[k];
+    int run = before + incl - sum;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int i = base + w * 256 + r * 32 + ln;
-    const int d = dg[r];
-    const unsigned mm = __match_any_sync(0xffffffffu, d);
-    if (d >= 0) {
-      const int pos = wcnt[w][d] + __popc(mm & ((1u << ln) - 1u));
-      kout[pos] = kin[i]; vout[pos] = vin[i];
-    }
-    __syncwarp();
-    if (d >= 0 && (__ffs(mm) - 1) == ln) wcnt[w][d] += __popc(mm);
-    __syncwarp();
+    for (int k = 0; k < 8; ++k) { const int i = base + tid * 8 + k; if (i < n) data[i] = run; run += v[k]; }
+    __syncthreads();
+    if (tid == kMapThreads - 1) s_carry = run;
+    __syncthreads();
   }
+  if (tid == 0 && total) *total = s_carry;
 }
 
-// step 6: group heads over the sorted keys (a group = one voxel of one touched cell)
-__global__ void __launch_bounds__(256) k_map_heads(MapDev m, int sb, int wtot) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= wtot) return;
-  const unsigned long long k = m.keys[sb][w];
-  m.head[w] = (k != kEmptyKey && (w == 0 || m.keys[sb][w - 1] != k)) ? 1 : 0;
+// exclusive scan of a long array by the whole grid: chunk sums -> scan of the sums (CTA 0) -> local scans
+__device__ void grid_scan_excl(cg::grid_group& grid, int* data, int n, int* tmp, int* total) {
+  constexpr int kChunkItems = kMapThreads * 8;
+  if (n <= 8 * kChunkItems) {   // short: one CTA does it (the condition is uniform over the grid)
+    if (blockIdx.x == 0) block_scan_excl(data, n, total);
+    grid.sync();
+    return;
+  }
+  __shared__ int s_w[8];
+  const int tid = threadIdx.x, ln = tid & 31, w = tid >> 5;
+  const int nchunks = (n + kChunkItems - 1) / kChunkItems;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int i = c * kChunkItems + tid * 8 + k; if (i < n) sum += data[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (ln == 0) s_w[w] = sum;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += s_w[k]; tmp[c] = t; }
+    __syncthreads();
+  }
+  grid.sync();
+  if (blockIdx.x == 0) block_scan_excl(tmp, nchunks, total);
+  grid.sync();
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    int v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int i = c * kChunkItems + tid * 8 + k; v[k] = i < n ? data[i] : 0; sum += v[k]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += t; }
+    if (ln == 31) s_w[w] = incl;
+    __syncthreads();
+    int before = tmp[c];
+    for (int k = 0; k < w; ++k) before += s_w[k];
+    int run = before + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int i = c * kChunkItems + tid * 8 + k; if (i < n) data[i] = run; run += v[k]; }
+    __syncthreads();
+  }
+  grid.sync();
 }
-// first group of every rank (binary search for the first key of the rank in the sorted keys)
-__global__ void __launch_bounds__(256) k_map_rankfirst(MapDev m, int sb, int wtot, int n_touched, int n_groups) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > n_touched) return;
-  if (r == n_touched) { m.group_first[r] = n_groups; return; }
-  const unsigned long long target = (unsigned long long)r << kRankShift;
-  int lo = 0, hi = wtot;  // first w with key >= target
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (m.keys[sb][mid] < target) lo = mid + 1; else hi = mid; }
-  m.group_first[r] = lo < wtot ? m.head[lo] : n_groups;   // head[] holds the exclusive scan = group index
-}
-// new per-cell counts (touched: its groups; untouched: unchanged) — then scanned into cell_newoff
-__global__ void __launch_bounds__(256) k_map_newcounts(MapDev m, int nc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  int cnt = m.cell_count[c];
-  if (m.touched[c]) { const int r = m.rank[c]; cnt = m.group_first[r + 1] - m.group_first[r]; }
-  m.cell_newoff[c] = cnt;
-}
-// step 7: centroids of the touched cells' voxels, sequential float accumulation in sorted order
-// (pcl::CentroidPoint: sum of x, y, z, intensity divided by the count as float).
-__global__ void __launch_bounds__(256) k_map_centroids(MapDev m, int cur, int sb, int wtot, int w_old, const int* head_flag_src) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= wtot) return;
-  const unsigned long long k = m.keys[sb][w];
-  if (k == kEmptyKey || (w > 0 && m.keys[sb][w - 1] == k)) return;   // not a group head
-  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-  int cnt = 0;
-  for (int u = w; u < wtot && m.keys[sb][u] == k; ++u) {
-    const int src = (int)m.vals[sb][u];
+
+__global__ void __launch_bounds__(kMapThreads) k_map_update(MapDev m, const float4* in, int n, int cur) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, ln = tid & 31, w = tid >> 5;
+  const int gtid = blockIdx.x * kMapThreads + tid, gsize = gridDim.x * kMapThreads;
+  MapState& st = *m.st;
+  __shared__ int s_a[kMapThreads], s_b[kMapThreads], s_c[kMapThreads];
+  __shared__ int s_carry3[3];
+  __shared__ int s_wcnt[8][256];
+
+  // ---- 1: transform, key, find-or-create hash slot (src/map.cc:93-118)
+  for (int i = gtid; i < n; i += gsize) {
+    const float4 sp = in[i];
     float4 p;
-    if (src < w_old) {
-      int lo = 0, hi = m.st->n_touched;
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.woff[mid] <= src) lo = mid; else hi = mid; }
-      p = m.pool[cur][m.cell_off[m.touched_list[lo]] + (src - m.woff[lo])];
-    } else p = m.newpts[src - w_old];
-    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
-    ++cnt;
+    p.x = xform_row(m.pose, sp.x, sp.y, sp.z); p.y = xform_row(m.pose + 4, sp.x, sp.y, sp.z); p.z = xform_row(m.pose + 8, sp.x, sp.y, sp.z);
+    p.w = sp.w;
+    m.newpts[i] = p;
+    m.pt_slot[i] = -1;
+    if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) { atomicAdd(&st.n_dropped, 1); continue; }
+    const int kx = cell_key_axis(p.x, m.inv_xy, m.xy, m.xy_half), ky = cell_key_axis(p.y, m.inv_xy, m.xy, m.xy_half);
+    const int kz = cell_key_axis(p.z, m.inv_z, m.zs, m.z_half);
+    unsigned long long key;
+    if (!pack_key(kx, ky, kz, &key)) { atomicOr(&st.error, 1); continue; }
+    unsigned slot = hash_key(key) & (unsigned)(m.hcap - 1);
+    for (;;) {
+      unsigned long long curk = ((volatile unsigned long long*)m.htab)[slot];
+      if (curk == kEmptyKey) {
+        curk = atomicCAS(&m.htab[slot], kEmptyKey, key);
+        if (curk == kEmptyKey) {  // created: remember it for id assignment
+          const int k = atomicAdd(&st.n_new_slots, 1);
+          if (k < m.cap_new) m.new_slots[k] = (int)slot; else atomicOr(&st.error, 2);
+          curk = key;
+        }
+      }
+      if (curk == key) break;
+      slot = (slot + 1) & (unsigned)(m.hcap - 1);
+    }
+    atomicMin(&m.hfirst[slot], i);
+    m.pt_slot[i] = (int)slot;
   }
-  const float fc = (float)cnt;
-  const int r = (int)(k >> kRankShift);
-  const int g = m.head[w];   // exclusive scan of the head flags = global group index
-  const int cid = m.touched_list[r];
-  m.pool[cur ^ 1][m.cell_newoff[cid] + (g - m.group_first[r])] = make_float4(__fdiv_rn(sx, fc), __fdiv_rn(sy, fc), __fdiv_rn(sz, fc), __fdiv_rn(si, fc));
-}
-// step 8: untouched cells move to their new offsets; counts/offsets are committed
-__global__ void __launch_bounds__(256) k_map_copy(MapDev m, int cur, int nc, int total_old) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_old) return;
-  int lo = 0, hi = nc;  // cell containing old point i
-  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.cell_off[mid] <= i) lo = mid; else hi = mid; }
-  if (m.touched[lo]) return;
-  m.pool[cur ^ 1][m.cell_newoff[lo] + (i - m.cell_off[lo])] = m.pool[cur][i];
-}
-__global__ void __launch_bounds__(256) k_map_commit(MapDev m, int nc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < nc) {
+  grid.sync();
+
+  // ---- 2: new cells get ids in order of first appearance in the input (cells_vector_ order)
+  if (gtid == 0) {
+    const int nn = min(st.n_new_slots, m.cap_new);
+    for (int a = 1; a < nn; ++a) {  // insertion sort by first input index (a handful of cells per update)
+      const int sl = m.new_slots[a], f = m.hfirst[sl];
+      int b = a - 1;
+      while (b >= 0 && m.hfirst[m.new_slots[b]] > f) { m.new_slots[b + 1] = m.new_slots[b]; --b; }
+      m.new_slots[b + 1] = sl;
+    }
+    const int lim = 1 << 20;
+    for (int a = 0; a < nn; ++a) {
+      const int sl = m.new_slots[a];
+      if (st.num_cells >= m.cap_cells) { st.error |= 2; break; }
+      const int id = st.num_cells++;
+      m.hval[sl] = id;
+      const unsigned long long k = m.htab[sl];
+      m.cell_key[id * 3 + 0] = (int)((k >> 42) & 0x1fffff) - lim;
+      m.cell_key[id * 3 + 1] = (int)((k >> 21) & 0x1fffff) - lim;
+      m.cell_key[id * 3 + 2] = (int)(k & 0x1fffff) - lim;
+      m.cell_count[id] = 0;
+    }
+    st.n_new_slots = 0;
+  }
+  grid.sync();
+
+  // ---- 3: point -> cell id, touched flags
+  for (int i = gtid; i < n; i += gsize) {
+    const int sl = m.pt_slot[i];
+    int cid = -1;
+    if (sl >= 0) { cid = m.hval[sl]; if (cid >= 0) m.touched[cid] = 1; }
+    m.pt_cell[i] = cid;
+  }
+  grid.sync();
+
+  // ---- 4 (CTA 0): prefix sums over the cells: old offsets, touched ranks, work offsets
+  const int nc = st.num_cells;
+  if (blockIdx.x == 0) {
+    if (tid < 3) s_carry3[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < nc; base += kMapThreads) {
+      const int c = base + tid;
+      const int cnt = c < nc ? m.cell_count[c] : 0, t = c < nc ? m.touched[c] : 0;
+      s_a[tid] = cnt; s_b[tid] = t; s_c[tid] = t ? cnt : 0;
+      __syncthreads();
+      for (int o = 1; o < kMapThreads; o <<= 1) {
+        const int va = tid >= o ? s_a[tid - o] : 0, vb = tid >= o ? s_b[tid - o] : 0, vc = tid >= o ? s_c[tid - o] : 0;
+        __syncthreads();
+        s_a[tid] += va; s_b[tid] += vb; s_c[tid] += vc;
+        __syncthreads();
+      }
+      if (c < nc) {
+        m.cell_off[c] = s_carry3[0] + s_a[tid] - cnt;
+        const int r = s_carry3[1] + s_b[tid] - t;
+        m.rank[c] = r;
+        if (t) { m.touched_list[r] = c; m.woff[r] = s_carry3[2] + s_c[tid] - cnt; }
+      }
+      __syncthreads();
+      if (tid == kMapThreads - 1) { s_carry3[0] += s_a[tid]; s_carry3[1] += s_b[tid]; s_carry3[2] += s_c[tid]; }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      m.cell_off[nc] = s_carry3[0];
+      m.woff[s_carry3[1]] = s_carry3[2];
+      st.n_touched = s_carry3[1];
+      st.w_old = s_carry3[2];
+    }
+  }
+  grid.sync();
+  const int n_touched = st.n_touched, w_old = st.w_old, wtot = w_old + n, total_old = m.cell_off[nc];
+
+  // ---- 5: sort keys of the work set [old points of touched cells (rank order, stored order) | new points]
+  for (int wi = gtid; wi < wtot; wi += gsize) {
+    float4 p; int r, cid;
+    if (wi < w_old) {
+      int lo = 0, hi = n_touched;  // last rank with woff[rank] <= wi
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.woff[mid] <= wi) lo = mid; else hi = mid; }
+      r = lo; cid = m.touched_list[r];
+      p = m.pool[cur][m.cell_off[cid] + (wi - m.woff[r])];
+    } else {
+      const int j = wi - w_old;
+      cid = m.pt_cell[j];
+      p = m.newpts[j];
+      if (cid < 0) { m.keys[0][wi] = kEmptyKey; m.vals[0][wi] = (unsigned)wi; continue; }  // dropped point: sorts last
+      r = m.rank[cid];
+    }
+    // lattice relative to the cell's lower corner (with a 2-voxel margin for float rounding at the faces)
+    const float fx = (float)((double)m.cell_key[cid * 3 + 0] - m.xy_half), fy = (float)((double)m.cell_key[cid * 3 + 1] - m.xy_half);
+    const float fz = (float)((double)m.cell_key[cid * 3 + 2] - m.z_half);
+    const int lx = lattice(p.x, m.inv_leaf) - (lattice(fx, m.inv_leaf) - 2), ly = lattice(p.y, m.inv_leaf) - (lattice(fy, m.inv_leaf) - 2);
+    const int lz = lattice(p.z, m.inv_leaf) - (lattice(fz, m.inv_leaf) - 2);
+    const int lim = 1 << kLatBits;
+    if (lx < 0 || lx >= lim || ly < 0 || ly >= lim || lz < 0 || lz >= lim) atomicOr(&st.error, 4);
+    m.keys[0][wi] = ((unsigned long long)r << kRankShift) | ((unsigned long long)(lz & (lim - 1)) << (2 * kLatBits)) |
+                    ((unsigned long long)(ly & (lim - 1)) << kLatBits) | (unsigned long long)(lx & (lim - 1));
+    m.vals[0][wi] = (unsigned)wi;
+  }
+  grid.sync();
+
+  // ---- stable LSD radix sort, 8-bit digits; key bits in use: 30 lattice bits + ceil(log2(n_touched)).
+  // (kEmptyKey = ~0 of dropped points has every processed digit at 255 and no valid key has, so it still sorts last.)
+  int bits = kRankShift;
+  while ((1 << (bits - kRankShift)) < n_touched) ++bits;
+  const int ntiles = (wtot + kTile - 1) / kTile;
+  int sb = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    const unsigned long long* kin = m.keys[sb];
+    const unsigned* vin = m.vals[sb];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      s_a[tid] = 0;
+      __syncthreads();
+      for (int k = tid; k < kTile; k += kMapThreads) {
+        const int i = tile * kTile + k;
+        if (i < wtot) atomicAdd(&s_a[(unsigned)(kin[i] >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      m.hist[tid * ntiles + tile] = s_a[tid];
+      __syncthreads();
+    }
+    grid.sync();
+    if (blockIdx.x == 0) block_scan_excl(m.hist, 256 * ntiles, nullptr);
+    grid.sync();
+    unsigned long long* kout = m.keys[sb ^ 1];
+    unsigned* vout = m.vals[sb ^ 1];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // each warp owns a contiguous 256-key run, 8 rounds of 32
+      for (int k = tid; k < 8 * 256; k += kMapThreads) (&s_wcnt[0][0])[k] = 0;
+      __syncthreads();
+      int dg[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = tile * kTile + w * 256 + r * 32 + ln;
+        const int dgt = i < wtot ? (int)((unsigned)(kin[i] >> shift) & 255u) : -1;
+        dg[r] = dgt;
+        const unsigned mm = __match_any_sync(0xffffffffu, dgt);
+        if (dgt >= 0 && (__ffs(mm) - 1) == ln) s_wcnt[w][dgt] += __popc(mm);
+        __syncwarp();
+      }
+      __syncthreads();
+      {
+        int run = m.hist[tid * ntiles + tile];
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) { const int c = s_wcnt[ww][tid]; s_wcnt[ww][tid] = run; run += c; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int i = tile * kTile + w * 256 + r * 32 + ln;
+        const int dgt = dg[r];
+        const unsigned mm = __match_any_sync(0xffffffffu, dgt);
+        if (dgt >= 0) {
+          const int pos = s_wcnt[w][dgt] + __popc(mm & ((1u << ln) - 1u));
+          kout[pos] = kin[i]; vout[pos] = vin[i];
+        }
+        __syncwarp();
+        if (dgt >= 0 && (__ffs(mm) - 1) == ln) s_wcnt[w][dgt] += __popc(mm);
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    grid.sync();
+    sb ^= 1;
+  }
+  const unsigned long long* skey = m.keys[sb];
+  const unsigned* sval = m.vals[sb];
+
+  // ---- 6: group heads over the sorted keys (a group = one voxel of one touched cell) -> exclusive scan = group index
+  for (int wi = gtid; wi < wtot; wi += gsize) {
+    const unsigned long long k = skey[wi];
+    m.head[wi] = (k != kEmptyKey && (wi == 0 || skey[wi - 1] != k)) ? 1 : 0;
+  }
+  grid.sync();
+  grid_scan_excl(grid, m.head, wtot, m.scan_tmp, &st.n_groups);
+  const int n_groups = st.n_groups;
+
+  // first group of every rank; new per-cell counts (touched: its groups; untouched: unchanged)
+  for (int r = gtid; r <= n_touched; r += gsize) {
+    if (r == n_touched) { m.group_first[r] = n_groups; continue; }
+    const unsigned long long target = (unsigned long long)r << kRankShift;
+    int lo = 0, hi = wtot;  // first position with key >= target
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey[mid] < target) lo = mid + 1; else hi = mid; }
+    m.group_first[r] = lo < wtot ? m.head[lo] : n_groups;
+  }
+  grid.sync();
+  for (int c = gtid; c < nc; c += gsize) {
+    int cnt = m.cell_count[c];
+    if (m.touched[c]) { const int r = m.rank[c]; cnt = m.group_first[r + 1] - m.group_first[r]; }
+    m.cell_newoff[c] = cnt;
+  }
+  grid.sync();
+  grid_scan_excl(grid, m.cell_newoff, nc, m.scan_tmp, &m.cell_newoff[nc]);
+
+  // ---- 7: centroids of the touched cells' voxels, sequential float accumulation in sorted order
+  // (pcl::CentroidPoint: sum of x, y, z, intensity divided by the count as float); 8: untouched cells move
+  for (int wi = gtid; wi < wtot; wi += gsize) {
+    const unsigned long long k = skey[wi];
+    if (k == kEmptyKey || (wi > 0 && skey[wi - 1] == k)) continue;   // not a group head
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int u = wi; u < wtot && skey[u] == k; ++u) {
+      const int src = (int)sval[u];
+      float4 p;
+      if (src < w_old) {
+        int lo = 0, hi = n_touched;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.woff[mid] <= src) lo = mid; else hi = mid; }
+        p = m.pool[cur][m.cell_off[m.touched_list[lo]] + (src - m.woff[lo])];
+      } else p = m.newpts[src - w_old];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+      ++cnt;
+    }
+    const float fc = (float)cnt;
+    const int r = (int)(k >> kRankShift);
+    const int g = m.head[wi];   // exclusive scan of the head flags = global group index
+    const int cid = m.touched_list[r];
+    m.pool[cur ^ 1][m.cell_newoff[cid] + (g - m.group_first[r])] = make_float4(__fdiv_rn(sx, fc), __fdiv_rn(sy, fc), __fdiv_rn(sz, fc), __fdiv_rn(si, fc));
+  }
+  for (int i = gtid; i < total_old; i += gsize) {
+    int lo = 0, hi = nc;  // cell containing old point i
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (m.cell_off[mid] <= i) lo = mid; else hi = mid; }
+    if (m.touched[lo]) continue;
+    m.pool[cur ^ 1][m.cell_newoff[lo] + (i - m.cell_off[lo])] = m.pool[cur][i];
+  }
+  grid.sync();
+
+  // ---- commit counts / offsets, reset the per-slot first-index scratch
+  for (int c = gtid; c < nc; c += gsize) {
     m.cell_count[c] = m.cell_newoff[c + 1] - m.cell_newoff[c];
     m.cell_off[c] = m.cell_newoff[c];
     m.touched[c] = 0;
   }
-  if (c == 0) { m.cell_off[nc] = m.cell_newoff[nc]; m.st->num_points = m.cell_newoff[nc]; }
-}
-__global__ void __launch_bounds__(256) k_map_reset_first(MapDev m, int n) {   // hfirst back to INT_MAX for the slots used
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && m.pt_slot[i] >= 0) m.hfirst[m.pt_slot[i]] = INT_MAX;
+  if (gtid == 0) { m.cell_off[nc] = m.cell_newoff[nc]; st.num_points = m.cell_newoff[nc]; }
+  for (int i = gtid; i < n; i += gsize)
+    if (m.pt_slot[i] >= 0) m.hfirst[m.pt_slot[i]] = INT_MAX;
 }
 
 // ---- extraction --------------------------------------------------------------------------------
-// keys3: nq query keys (reference ints).  seg[q] = {offset, count} of the cell or {0, 0}.
-__global__ void k_map_lookup(MapDev m, const int* keys3, int nq, int* seg_off, int* seg_cnt) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  unsigned long long key;
-  int off = 0, cnt = 0;
-  if (pack_key(keys3[q * 3], keys3[q * 3 + 1], keys3[q * 3 + 2], &key)) {
-    const int s = find_slot(m, key);
-    if (s >= 0) { const int cid = m.hval[s]; if (cid >= 0) { off = m.cell_off[cid]; cnt = m.cell_count[cid]; } }
+// Map::getLocalMap in one launch.  keys3: nq < 4096 query keys (reference ints, duplicates allowed).
+// Every CTA looks all of them up and scans the counts in shared memory (a few dozen cells: cheaper than
+// a grid barrier), then gathers its share of the concatenated cloud.  *total_out = its size; nothing is
+// written when it exceeds `cap`.  `out` may be device memory or mapped pinned host memory.
+constexpr int kMaxQueryCells = 4096;
+__global__ void __launch_bounds__(256) k_map_local(MapDev m, const float4* pool, const int* keys3, int nq, float4* out, int cap, int* total_out) {
+  __shared__ int s_off[kMaxQueryCells], s_pre[kMaxQueryCells + 1];
+  __shared__ int s_wtot[8];
+  const int tid = threadIdx.x, ln = tid & 31, w = tid >> 5;
+  constexpr int kPer = kMaxQueryCells / 256;   // consecutive queries per thread
+  int cnt[kPer], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int q = tid * kPer + k;
+    int off = 0, c = 0;
+    unsigned long long key;
+    if (q < nq && pack_key(keys3[q * 3], keys3[q * 3 + 1], keys3[q * 3 + 2], &key)) {
+      const int sl = find_slot(m, key);
+      if (sl >= 0) { const int cid = m.hval[sl]; if (cid >= 0) { off = m.cell_off[cid]; c = m.cell_count[cid]; } }
+    }
+    if (q < kMaxQueryCells) s_off[q] = off;
+    cnt[k] = c; sum += c;
   }
-  seg_off[q] = off; seg_cnt[q] = cnt;
-}
-__global__ void __launch_bounds__(256) k_map_gather(const float4* pool, const int* seg_off, const int* seg_pre, int nq, int total, float4* out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int lo = 0, hi = nq;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_pre[mid] <= i) lo = mid; else hi = mid; }
-    out[i] = pool[seg_off[lo] + (i - seg_pre[lo])];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += t; }
+  if (ln == 31) s_wtot[w] = incl;
+  __syncthreads();
+  int run = incl - sum;
+  for (int k = 0; k < w; ++k) run += s_wtot[k];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) { s_pre[tid * kPer + k] = run; run += cnt[k]; }
+  if (tid == 255) s_pre[kMaxQueryCells] = run;
+  __syncthreads();
+  const int total = s_pre[kMaxQueryCells];
+  if (blockIdx.x == 0 && tid == 0) *total_out = total;
+  if (total > cap || out == nullptr) return;
+  for (int i = blockIdx.x * 256 + tid; i < total; i += gridDim.x * 256) {
+    int lo = 0, hi = nq;   // last query whose prefix is <= i (empty cells share a prefix: the last one wins, it holds the point)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+    out[i] = pool[s_off[lo] + (i - s_pre[lo])];
   }
 }
 
@@ -463,10 +523,16 @@ struct liodom_map {
   std::vector<void*> allocs;
   std::string err;
   float4* stage_in = nullptr;    // device copy of the input cloud
-  int* q_keys = nullptr;         // device scratch of getLocalMap
-  int* q_off = nullptr; int* q_cnt = nullptr; int* q_pre = nullptr;
+  int* q_keys = nullptr;         // device scratch of getLocalMap: query keys
+  int* q_total = nullptr;        // ... and the size of the gathered cloud
+  int* h_total = nullptr;        // pinned
+  float* h_gather = nullptr;     // pinned + mapped window the gather kernel writes host results into
+  float4* h_gather_dev = nullptr;
+  int h_gather_cap = 0;          // points
+  std::vector<int> h_keys;
   float4* gather_out = nullptr;  // [cap_points]
   int h_cells = 0, h_points = 0;
+  int coop_blocks = 0;           // grid of the cooperative update kernel (every CTA resident)
   long long launches = 0;
 };
 
@@ -492,16 +558,6 @@ static cudaError_t malloc_dev(liodom_map* c, T** p, size_t count, int fill = 0) 
   e = cudaMemsetAsync(q, fill, count * sizeof(T) + 256, c->stream);
   *p = static_cast<T*>(q);
   return e;
-}
-
-// exclusive scan of data[0..n) in place (n+1-th element = total written by the caller's layout)
-static void scan_inplace(liodom_map* c, int* data, int n, int* total) {
-  if (n <= 1 << 16) { k_scan1<<<1, 1024, 0, c->stream>>>(data, n, total); c->launches += 1; return; }
-  const int nb = (n + 4095) / 4096;
-  k_scan_blocksum<<<nb, 1024, 0, c->stream>>>(data, n, c->m.scan_tmp);
-  k_scan1<<<1, 1024, 0, c->stream>>>(c->m.scan_tmp, nb, total);
-  k_scan_local<<<nb, 1024, 0, c->stream>>>(data, n, c->m.scan_tmp);
-  c->launches += 3;
 }
 
 extern "C" {
@@ -565,15 +621,24 @@ int liodom_map_create(double voxel_xysize, double voxel_zsize, double resolution
   MCC(malloc_dev(c, &m.pt_cell, (size_t)m.cap_new));
   MCC(malloc_dev(c, &m.head, capw));
   MCC(malloc_dev(c, &m.hist, (size_t)256 * c->nblk_max));
-  MCC(malloc_dev(c, &m.scan_tmp, capw / 4096 + 8));
+  MCC(malloc_dev(c, &m.scan_tmp, capw / 2048 + 8));
   MCC(malloc_dev(c, &m.st, 1));
   MCC(malloc_dev(c, &m.pose, 12));
   MCC(malloc_dev(c, &c->stage_in, (size_t)m.cap_new));
   MCC(malloc_dev(c, &c->q_keys, 3 * 4096));
-  MCC(malloc_dev(c, &c->q_off, 4096));
-  MCC(malloc_dev(c, &c->q_cnt, 4096));
-  MCC(malloc_dev(c, &c->q_pre, 4097));
+  MCC(malloc_dev(c, &c->q_total, 1));
+  MCC(cudaMallocHost(&c->h_total, sizeof(int)));
+  c->h_gather_cap = std::min(m.cap_points, 1 << 19);   // 8 MB window; larger local maps take the device path
+  MCC(cudaHostAlloc(&c->h_gather, (size_t)c->h_gather_cap * 16, cudaHostAllocMapped));
+  { void* dp = nullptr; MCC(cudaHostGetDevicePointer(&dp, c->h_gather, 0)); c->h_gather_dev = static_cast<float4*>(dp); }
   MCC(malloc_dev(c, &c->gather_out, (size_t)m.cap_points));
+  {
+    int per_sm = 0, sms = 0;
+    MCC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map_update, kMapThreads, 0));
+    MCC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) { mfail(nullptr, LIODOM_E_CUDA, "k_map_update cannot be made resident"); liodom_map_destroy(c); return LIODOM_E_CUDA; }
+    c->coop_blocks = sms;   // one CTA per SM: the phases are short, more CTAs only lengthen the grid barriers
+  }
   MCC(cudaStreamSynchronize(c->stream));
 #undef MCC
   *out = c;
@@ -585,66 +650,37 @@ void liodom_map_destroy(liodom_map* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void* p : c->allocs) cudaFree(p);
+  if (c->h_total) cudaFreeHost(c->h_total);
+  if (c->h_gather) cudaFreeHost(c->h_gather);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
-// Map::updateMap (src/map.cc:90-129)
+// Map::updateMap (src/map.cc:90-129): stage the cloud and the pose, ONE cooperative launch, one read-back.
 int liodom_map_update(liodom_map* c, const float* pts_xyzi, int n, const double* pose16) {
   if (!c || !pose16 || n < 0) return mfail(c, LIODOM_E_INVALID, "bad arguments");
   MCK(cudaSetDevice(c->device));
   MapDev& m = c->m;
   if (n > m.cap_new) return mfail(c, LIODOM_E_CAPACITY, "cloud of %d points exceeds the per-update capacity %d", n, m.cap_new);
   if (n == 0) return 0;
+  if ((size_t)c->h_points + n > (size_t)m.cap_points)
+    return mfail(c, LIODOM_E_CAPACITY, "map of %d points + %d new exceeds max_points %d", c->h_points, n, m.cap_points);
   cudaStream_t s = c->stream;
   MCK(cudaMemcpyAsync(c->stage_in, pts_xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, s));
   MCK(cudaMemcpyAsync(m.pose, pose16, sizeof(double) * 12, cudaMemcpyHostToDevice, s));
-  const int gb = (n + 255) / 256;
-  k_map_insert<<<gb, 256, 0, s>>>(m, c->stage_in, n);
-  k_map_assign<<<1, 32, 0, s>>>(m);
-  k_map_mark<<<gb, 256, 0, s>>>(m, n);
-  k_map_plan<<<1, 1024, 0, s>>>(m);
-  c->launches += 4;
+  const float4* in = c->stage_in;
+  int cur = c->cur;
+  void* args[] = {(void*)&m, (void*)&in, (void*)&n, (void*)&cur};
+  MCK(cudaLaunchCooperativeKernel((const void*)k_map_update, dim3(c->coop_blocks), dim3(kMapThreads), args, 0, s));
+  c->launches += 1;
   MapState st;
   MCK(cudaMemcpyAsync(&st, m.st, sizeof(st), cudaMemcpyDeviceToHost, s));
   MCK(cudaStreamSynchronize(s));
-  if (st.error & 1) return mfail(c, LIODOM_E_INVALID, "map coordinates beyond the +-2^20 m key range");
-  if (st.error & 2) return mfail(c, LIODOM_E_CAPACITY, "cell capacity exceeded (%d cells)", m.cap_cells);
-  const int wtot = st.w_old + n, nc = st.num_cells, total_old = st.num_points;
-  if ((size_t)total_old + n > (size_t)m.cap_points) return mfail(c, LIODOM_E_CAPACITY, "map of %d points + %d new exceeds max_points %d", total_old, n, m.cap_points);
-  k_map_workkeys<<<(wtot + 255) / 256, 256, 0, s>>>(m, c->cur, st.w_old, n, st.n_touched);
-  c->launches += 1;
-  // key bits in use: 30 lattice bits + ceil(log2(n_touched))
-  int bits = kRankShift;
-  while ((1 << (bits - kRankShift)) < st.n_touched) ++bits;
-  const int nblk = (wtot + kTile - 1) / kTile;
-  int sb = 0;
-  for (int shift = 0; shift < bits; shift += 8) {
-    k_rs_hist<<<nblk, 256, 0, s>>>(m.keys[sb], wtot, shift, m.hist, nblk);
-    scan_inplace(c, m.hist, 256 * nblk, nullptr);
-    k_rs_scatter<<<nblk, 256, 0, s>>>(m.keys[sb], m.vals[sb], m.keys[sb ^ 1], m.vals[sb ^ 1], wtot, shift, m.hist, nblk);
-    c->launches += 2;
-    sb ^= 1;
-  }
-  k_map_heads<<<(wtot + 255) / 256, 256, 0, s>>>(m, sb, wtot);
-  scan_inplace(c, m.head, wtot, &m.st->n_groups);
-  int n_groups = 0;
-  MCK(cudaMemcpyAsync(&n_groups, &m.st->n_groups, sizeof(int), cudaMemcpyDeviceToHost, s));
-  MCK(cudaStreamSynchronize(s));
-  k_map_rankfirst<<<(st.n_touched + 256) / 256, 256, 0, s>>>(m, sb, wtot, st.n_touched, n_groups);
-  k_map_newcounts<<<(nc + 255) / 256, 256, 0, s>>>(m, nc);
-  scan_inplace(c, m.cell_newoff, nc, &m.cell_newoff[nc]);
-  k_map_centroids<<<(wtot + 255) / 256, 256, 0, s>>>(m, c->cur, sb, wtot, st.w_old, nullptr);
-  if (total_old > 0) k_map_copy<<<(total_old + 255) / 256, 256, 0, s>>>(m, c->cur, nc, total_old);
-  k_map_commit<<<(nc + 255) / 256, 256, 0, s>>>(m, nc);
-  k_map_reset_first<<<gb, 256, 0, s>>>(m, n);
-  c->launches += 7;
-  MCK(cudaGetLastError());
-  MCK(cudaMemcpyAsync(&st, m.st, sizeof(st), cudaMemcpyDeviceToHost, s));
-  MCK(cudaStreamSynchronize(s));
-  if (st.error & 4) return mfail(c, LIODOM_E_INVALID, "voxel lattice overflow inside a cell (cell size / resolution too large)");
   c->cur ^= 1;
   c->h_cells = st.num_cells; c->h_points = st.num_points;
+  if (st.error & 1) return mfail(c, LIODOM_E_INVALID, "map coordinates beyond the +-2^20 m key range");
+  if (st.error & 2) return mfail(c, LIODOM_E_CAPACITY, "cell capacity exceeded (%d cells)", m.cap_cells);
+  if (st.error & 4) return mfail(c, LIODOM_E_INVALID, "voxel lattice overflow inside a cell (cell size / resolution too large)");
   return 0;
 }
 
@@ -671,12 +707,13 @@ int liodom_map_get(liodom_map* c, float* xyzi, int cap, int* n_points) {
 // Map::getLocalMap (src/map.cc:141-189).  The key list is host integer arithmetic restated from
 // the reference (translation truncated to int; the z loop bounds use voxel_xysize_ and `int += double`).
 // The cloud is gathered on the device into `dev_out` (capacity `cap` points); returns its size.
-static int map_local_to_device(liodom_map* c, const double* pose16, int cells_xy, int cells_z, float4* dev_out, int cap, int* n_points) {
+static int map_local_keys(liodom_map* c, const double* pose16, int cells_xy, int cells_z, int* nq_out) {
   const MapDev& m = c->m;
   const int x = (int)pose16[3], y = (int)pose16[7], z = (int)pose16[11];
   const int vx = (int)(std::floor(x * m.inv_xy) * m.xy + m.xy_half), vy = (int)(std::floor(y * m.inv_xy) * m.xy + m.xy_half);
   const int vz = (int)(std::floor(z * m.inv_z) * m.zs + m.z_half);
-  std::vector<int> keys;
+  std::vector<int>& keys = c->h_keys;
+  keys.clear();
   const int init_x = (int)(vx - cells_xy * m.xy), end_x = (int)(vx + cells_xy * m.xy);
   const int init_y = (int)(vy - cells_xy * m.xy), end_y = (int)(vy + cells_xy * m.xy);
   for (int i = init_x; i <= end_x && keys.size() < 3 * 4096; i = (int)(i + m.xy))
@@ -684,24 +721,26 @@ static int map_local_to_device(liodom_map* c, const double* pose16, int cells_xy
   const int init_z = (int)(vz - cells_z * m.xy), end_z = (int)(vz + cells_z * m.xy);
   for (int i = init_z; i <= end_z && keys.size() < 3 * 4096; i = (int)(i + m.zs)) { keys.push_back(vx); keys.push_back(vy); keys.push_back(i); }
   const int nq = (int)keys.size() / 3;
-  if (nq >= 4096) return mfail(c, LIODOM_E_CAPACITY, "getLocalMap asks for %d cells (limit 4095)", nq);
+  if (nq >= kMaxQueryCells) return mfail(c, LIODOM_E_CAPACITY, "getLocalMap asks for %d cells (limit %d)", nq, kMaxQueryCells - 1);
   MCK(cudaMemcpyAsync(c->q_keys, keys.data(), sizeof(int) * keys.size(), cudaMemcpyHostToDevice, c->stream));
-  k_map_lookup<<<(nq + 127) / 128, 128, 0, c->stream>>>(m, c->q_keys, nq, c->q_off, c->q_cnt);
-  MCK(cudaMemcpyAsync(c->q_pre, c->q_cnt, sizeof(int) * nq, cudaMemcpyDeviceToDevice, c->stream));
-  k_scan1<<<1, 1024, 0, c->stream>>>(c->q_pre, nq, c->q_pre + nq);
-  int total = 0;
-  MCK(cudaMemcpyAsync(&total, c->q_pre + nq, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  *nq_out = nq;
+  return 0;
+}
+
+// The cloud is gathered into `out` (device memory, or mapped pinned host memory) of capacity `cap` points;
+// one launch, one synchronisation.  *n_points = its size even when it does not fit (then nothing is written).
+static int map_local_gather(liodom_map* c, const double* pose16, int cells_xy, int cells_z, float4* out, int cap, int* n_points) {
+  int nq = 0;
+  int rc = map_local_keys(c, pose16, cells_xy, cells_z, &nq);
+  if (rc) return rc;
+  int blocks = (std::min(c->h_points, std::max(cap, 1)) + 4095) / 4096;
+  blocks = std::max(1, std::min(blocks, 148));
+  k_map_local<<<blocks, 256, 0, c->stream>>>(c->m, c->m.pool[c->cur], c->q_keys, nq, out, cap, c->q_total);
+  c->launches += 1;
+  MCK(cudaGetLastError());
+  MCK(cudaMemcpyAsync(c->h_total, c->q_total, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   MCK(cudaStreamSynchronize(c->stream));
-  c->launches += 2;
-  if (n_points) *n_points = total;
-  if (dev_out && total > 0) {
-    if (cap < total) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
-    int blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    k_map_gather<<<blocks, 256, 0, c->stream>>>(m.pool[c->cur], c->q_off, c->q_pre, nq, total, dev_out);
-    c->launches += 1;
-    MCK(cudaGetLastError());
-    MCK(cudaStreamSynchronize(c->stream));
-  }
+  if (n_points) *n_points = *c->h_total;
   return 0;
 }
 
@@ -709,26 +748,32 @@ int liodom_map_get_local(liodom_map* c, const double* pose16, int cells_xy, int 
   if (!c || !pose16) return mfail(c, LIODOM_E_INVALID, "bad arguments");
   MCK(cudaSetDevice(c->device));
   int total = 0;
-  int rc = map_local_to_device(c, pose16, cells_xy, cells_z, nullptr, 0, &total);
+  // first try: straight into the mapped pinned buffer (one launch, one synchronisation, one host memcpy)
+  int rc = map_local_gather(c, pose16, cells_xy, cells_z, xyzi ? c->h_gather_dev : nullptr, xyzi ? std::min(cap, c->h_gather_cap) : 0, &total);
   if (rc) return rc;
   if (n_points) *n_points = total;
-  if (xyzi && total > 0) {
-    if (cap < total) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
-    if (total > c->m.cap_points) return mfail(c, LIODOM_E_CAPACITY, "local map of %d points exceeds max_points (duplicated centre cell)", total);
-    rc = map_local_to_device(c, pose16, cells_xy, cells_z, c->gather_out, c->m.cap_points, &total);
-    if (rc) return rc;
-    MCK(cudaMemcpyAsync(xyzi, c->gather_out, (size_t)total * 16, cudaMemcpyDeviceToHost, c->stream));
-    MCK(cudaStreamSynchronize(c->stream));
-  }
+  if (!xyzi || total == 0) return 0;
+  if (cap < total) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
+  if (total <= c->h_gather_cap) { std::memcpy(xyzi, c->h_gather, (size_t)total * 16); return 0; }
+  // larger than the pinned window: gather on the device, then copy
+  if (total > c->m.cap_points) return mfail(c, LIODOM_E_CAPACITY, "local map of %d points exceeds max_points (duplicated centre cell)", total);
+  rc = map_local_gather(c, pose16, cells_xy, cells_z, c->gather_out, c->m.cap_points, &total);
+  if (rc) return rc;
+  MCK(cudaMemcpyAsync(xyzi, c->gather_out, (size_t)total * 16, cudaMemcpyDeviceToHost, c->stream));
+  MCK(cudaStreamSynchronize(c->stream));
   return 0;
 }
-
 // Same, but the cloud stays on the device (`dev_xyzi`: device pointer, e.g. the buffer returned by
 // liodom_received_map_buffer): the map -> odometry feedback of mapping=1 without a host round trip.
 int liodom_map_get_local_device(liodom_map* c, const double* pose16, int cells_xy, int cells_z, void* dev_xyzi, int cap, int* n_points) {
   if (!c || !pose16 || !dev_xyzi) return mfail(c, LIODOM_E_INVALID, "bad arguments");
   MCK(cudaSetDevice(c->device));
-  return map_local_to_device(c, pose16, cells_xy, cells_z, static_cast<float4*>(dev_xyzi), cap, n_points);
+  int total = 0;
+  const int rc = map_local_gather(c, pose16, cells_xy, cells_z, static_cast<float4*>(dev_xyzi), cap, &total);
+  if (rc) return rc;
+  if (n_points) *n_points = total;
+  if (total > cap) return mfail(c, LIODOM_E_CAPACITY, "output capacity %d < local map size %d", cap, total);
+  return 0;
 }
 
 int liodom_map_cells(liodom_map* c, int32_t* keys3, int32_t* counts, int cap, int* n_cells) {
