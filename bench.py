@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("LIODOM_BENCH_LANES", "128")),
                     help="independent sequences per GPU processed by one step")
     ap.add_argument("--sensor", default="hdl64")
+    ap.add_argument("--config", default="c1", choices=["c1", "c2", "c3"],
+                    help="c1: the headline workload (launch/liodom.launch); c2 / c3: the other BASELINE.json shapes "
+                         "(OS1-128 organised clouds; scan_regions/edges_per_region doubled, prev_frames=20), for profiles/ only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-pass", action="store_true")
     return ap.parse_args()
@@ -151,11 +154,26 @@ def run_b200(args):
     nframes = W + K
     nseq = min(B, N_SEEDS)
     t0 = time.time()
+    width = height = 0
+    kw_cfg = {}
+    workload = ("C1: HDL-64-shaped ray-cast urban sequences (~118k pts/scan), launch/liodom.launch params "
+                "(scan_regions=8, edges_per_region=10, prev_frames=15, range 3-75 m), extract+register")
+    if args.config == "c2":
+        from liodom_b200 import synth
+        args.sensor = "os1_128"
+        width, height = synth.sensor_shape("os1_128")
+        kw_cfg = dict(lidar_type=1, scan_lines=128)
+        workload = ("C2: OS1-128-shaped organised clouds (128 x 2048 slots), launch/liodom_ouster.launch params with "
+                    "scan_lines=128, extract+register")
+    elif args.config == "c3":
+        kw_cfg = dict(scan_regions=16, edges_per_region=20, prev_frames=20)
+        workload = ("C3: C1 scans with scan_regions=16, edges_per_region=20, prev_frames=20 (large local map), extract+register")
     seqs = make_sequences(args.sensor, rank, nseq, nframes, world)
     gen_s = time.time() - t0
     npts = np.array([[len(seqs[s][f]) for f in range(nframes)] for s in range(nseq)])
-    max_points = 131072 if args.sensor == "hdl64" else 1 << 20
+    max_points = 131072 if args.sensor == "hdl64" else (262144 if args.sensor == "os1_128" else 1 << 20)
     kw = dict(prev_frames=15, max_points=max_points)   # launch/liodom.launch:17-31
+    kw.update(kw_cfg)
 
     # inputs resident in HBM: one tensor per (lane, frame).  Lanes that replay the same synthetic sequence
     # still get their own copy, so that no lane finds its scan in L2 because another lane just read it.
@@ -189,7 +207,7 @@ def run_b200(args):
     def step_dev(f):
         ptrs = [dev_scans[l][f].data_ptr() for l in range(B)]
         cnts = [int(npts[l % nseq][f]) for l in range(B)]
-        ctx.scan_batch_ptrs(ptrs, cnts, BYTES_PER_POINT, on_device=True)
+        ctx.scan_batch_ptrs(ptrs, cnts, BYTES_PER_POINT, width=width, height=height, on_device=True)
 
     for f in range(W):
         step_dev(f)
@@ -282,7 +300,7 @@ def run_b200(args):
 
     def enqueue_e2e(f):
         cnts = [int(npts[l % nseq][f]) for l in range(B)]
-        ctx.scan_batch_ptrs(host_ptrs[f], cnts, BYTES_PER_POINT, on_device=False)
+        ctx.scan_batch_ptrs(host_ptrs[f], cnts, BYTES_PER_POINT, width=width, height=height, on_device=False)
 
     for f in range(W):
         enqueue_e2e(f)
@@ -327,7 +345,7 @@ def run_b200(args):
     # ---------------- CPU baseline (restated reference path, rank 0, N=1 only) --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_single_stream(seqs, budget_s=15.0)
+        cpu = cpu_baseline_single_stream(seqs, budget_s=15.0, okw=dict(dict(prev_frames=15), **kw_cfg), width=width, height=height, name=args.config.upper())
 
     if world > 1:
         dist.barrier()
@@ -338,8 +356,7 @@ def run_b200(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 selection/kNN, f64 gates+LM", "data": "synthetic",
-        "config": {"workload": "C1: HDL-64-shaped ray-cast urban sequences (~118k pts/scan), launch/liodom.launch params "
-                               "(scan_regions=8, edges_per_region=10, prev_frames=15, range 3-75 m), extract+register",
+        "config": {"workload": workload,
                    "lanes_per_gpu": B, "distinct_sequences_per_gpu": nseq, "points_per_scan": int(npts.mean()),
                    "sharding": "independent sequences per GPU, no collective",
                    "l2": "every step reads a distinct scan batch at distinct addresses per lane (%d MB/step/GPU; %d MB over the run; L2 is 126 MB), uploaded before timing"
@@ -361,24 +378,24 @@ def run_b200(args):
     emit(out)
 
 
-def cpu_baseline_single_stream(seqs, budget_s):
+def cpu_baseline_single_stream(seqs, budget_s, okw=None, width=0, height=0, name="C1"):
     """The oracle port with the reference's own threading (OpenMP curvature loop with
     max(2, nthreads-5) threads, solver threads = nproc), one stream after another."""
     import oracle
-    op = oracle.make_params(prev_frames=15)
+    op = oracle.make_params(**(okw or dict(prev_frames=15)))
     n = 0
     t0 = time.perf_counter()
     stage = np.zeros(5)
     for scans in seqs:
-        _, st, _ = oracle.run_sequence(op, scans)
+        _, st, _ = oracle.run_sequence(op, scans, width, height)
         stage += st
         n += len(scans)
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     return {"value": round(n / dt, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-            "sample": "%d scans of the same C1 sequences, single stream, reference threading (restated CPU path; "
-                      "the reference binary needs ROS/PCL/Ceres and cannot be built here)" % n,
+            "sample": "%d scans of the same %s sequences, single stream, reference threading (restated CPU path; "
+                      "the reference binary needs ROS/PCL/Ceres and cannot be built here)" % (n, name),
             "ms_per_scan": round(dt / n * 1e3, 3),
             "stage_ms_per_scan": {k: round(v / n / 1e3, 3) for k, v in zip(("split", "extract", "associate", "solve", "window"), stage)}}
 
