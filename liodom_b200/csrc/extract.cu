@@ -64,7 +64,52 @@ __device__ __forceinline__ bool near_int(double v) { return fabs(v - rint(v)) < 
 
 // Returns ring id or -1. `amb` is set when a bin decision sits within kAmbTol of a boundary
 // (such a point could land in the other bin under a different libm).
+// FP32 screening of the same decisions: when every comparison of the reference's double arithmetic (range
+// gates, branch and reject thresholds, bin truncation) is further from its threshold than the FP32 error can
+// reach, the float result IS the double result and the ~100 FP64 operations (sqrt, division, atan) are skipped.
+// Error budget: sqrtf / division / atanf are within 2 ulp each, so the angle is within 1e-6 rad = 6e-5 deg and the
+// bin coordinate v (slope <= 3 per degree) within 2e-4; the margins below are 5x that.  Returns false when a
+// decision is too close to call (then the double path decides, as before).
+__device__ __forceinline__ bool ring_of_point_fast(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, int* id_out) {
+  const float d = sqrtf(xf * xf + yf * yf);
+  const float minr = (float)p.min_range, maxr = (float)p.max_range;
+  if (!(isfinite(xf) && isfinite(yf) && isfinite(zf))) { *id_out = -1; return true; }
+  const float mr = 1e-3f;                                   // metres; float error at 75 m is 1e-5
+  if (fabsf(d - minr) < mr || fabsf(d - maxr) < mr) return false;
+  if (d > maxr || d < minr) { *id_out = -1; return true; }
+  if (p.lidar_type == 1) { const int row = i / sc.width; *id_out = row < p.scan_lines ? row : -1; return true; }
+  const float ang = atanf(zf / d) * 57.295779513f;
+  const float ma = 3e-4f, mv = 1e-3f;
+  int id;
+  if (p.scan_lines == 64) {
+    if (fabsf(ang + 8.83f) < ma || fabsf(ang - 2.0f) < ma || fabsf(ang + 24.33f) < ma) return false;
+    if (ang > 2.0f || ang < -24.33f) { *id_out = -1; return true; }
+    const float v = ang >= -8.83f ? (2.0f - ang) * 3.0f + 0.5f : (-8.83f - ang) * 2.0f + 0.5f;
+    if (fabsf(v - rintf(v)) < mv) return false;
+    id = (ang >= -8.83f ? 0 : 32) + (int)v;
+    if (id > 63 || id < 0) id = -1;
+  } else if (p.scan_lines == 32) {
+    const float v = (ang + 30.666666f) * 0.75f;
+    if (fabsf(v - rintf(v)) < mv) return false;
+    id = (int)v;
+    if (id > 31 || id < 0) id = -1;
+  } else if (p.scan_lines == 16) {
+    const float v = (ang + 15.0f) * 0.5f + 0.5f;
+    if (fabsf(v - rintf(v)) < mv) return false;
+    id = (int)v;
+    if (id > 15 || id < 0) id = -1;
+  } else {
+    return false;
+  }
+  *id_out = id;
+  return true;
+}
+
 __device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, bool& amb) {
+  {
+    int fast_id;
+    if (ring_of_point_fast(p, sc, i, xf, yf, zf, &fast_id)) { amb = false; return fast_id; }
+  }
   const double x = xf, y = yf, z = zf;
   bool valid = isfinite(x) && isfinite(y) && isfinite(z);
   const double dist = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));

@@ -170,3 +170,42 @@ def test_extract_capacity_and_errors(cuda_lib):
         api.Context(scan_lines=48)   # "Invalid scan lines" (src/feature_extractor.cc:150)
     with pytest.raises(api.LiodomError):
         api.Context(lidar_type=2)    # "Incorrect Lidar type" (:177)
+
+
+@pytest.mark.parametrize("lines", [64, 32, 16])
+def test_split_points_near_bin_and_range_boundaries(cuda_lib, lines):
+    """The ring split screens every decision in FP32 and falls back to the reference's double arithmetic
+    when a threshold is within reach of the float error.  Points placed at 1e-7 .. 1e-2 degrees from every
+    bin edge and 1e-6 .. 1e-2 m from the range gates must get the oracle's ring ids."""
+    rng = np.random.default_rng(100 + lines)
+    if lines == 64:
+        edges = [2.0 - (k - 0.5) / 3.0 for k in range(0, 34)] + [-8.83 - (k - 0.5) / 2.0 for k in range(0, 33)] + [2.0, -8.83, -24.33]
+    elif lines == 32:
+        edges = [k * 4.0 / 3.0 - 92.0 / 3.0 for k in range(-1, 34)]
+    else:
+        edges = [2.0 * (k - 0.5) - 15.0 for k in range(-1, 18)]
+    pts = []
+    for e in edges:
+        for d in (1e-2, 1e-3, 5e-4, 2e-4, 1e-5, 1e-7):
+            for sgn in (-1.0, 1.0):
+                ang = np.deg2rad(e + sgn * d)
+                az = rng.uniform(0, 2 * np.pi)
+                r = rng.uniform(5.0, 60.0)
+                pts.append([r * np.cos(az), r * np.sin(az), r * np.tan(ang), 0.5])
+    for gate in (3.0, 75.0):
+        for d in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6):
+            for sgn in (-1.0, 1.0):
+                az = rng.uniform(0, 2 * np.pi)
+                r = gate + sgn * d
+                pts.append([r * np.cos(az), r * np.sin(az), r * np.tan(np.deg2rad(-3.1)), 0.25])
+    s = np.array(pts, np.float32)
+    op = oracle.make_params(scan_lines=lines)
+    ctx = api.Context(scan_lines=lines, max_points=4096)
+    g = ctx.split(s)
+    o = oracle.split(op, s)
+    # device atan (<= 2 ulp) and glibc atan (<= 1 ulp) may differ within 1e-12 of an edge: those are counted, not compared
+    assert g["n_ambiguous"] <= 4
+    diff = np.nonzero(g["ring_of_point"] != o["ring_of_point"])[0]
+    assert len(diff) <= g["n_ambiguous"], (len(diff), g["n_ambiguous"])
+    assert (g["ring_of_point"] >= 0).sum() > len(s) // 2
+    ctx.close()
