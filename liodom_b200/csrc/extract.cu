@@ -6,6 +6,7 @@
 // (the reference is built without -march, i.e. SSE2 without FMA, CMakeLists.txt:13).
 #include "common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace liodom {
 
@@ -583,12 +584,23 @@ static size_t extract_smem_bytes(const DevParams& p, int ring_cap) {
   return (size_t)ring_cap * 24 + (size_t)wcap * 8 + (size_t)p.scan_regions * (p.edges_per_region + 1) * 4 + (size_t)p.scan_regions * 4 + 16;
 }
 
+// Ring points kept in shared memory by k_extract.  The kernel alternates block-wide phases (curvature, per-warp
+// region selection, a one-warp fix-up, emission), so resident CTAs per SM matter: the capacity is the largest one
+// that still lets k CTAs share an SM's 228 KB, for the largest k whose capacity covers the expected ring length
+// (max_points / scan_lines + 5 %; 4 CTAs/SM for HDL-64 and OS1-128: extract 0.44 -> 0.39 ms/step at 128 lanes).
+// Longer rings are still handled, through the global-memory path.
 int extract_ring_cap(const DevParams& p) {
-  long want = ((long)p.Ncap * 5 / 4) / p.scan_lines;
-  want = (want + 255) / 256 * 256;
-  if (want < 1024) want = 1024;
-  if (want > kRingSmemCap) want = kRingSmemCap;
-  return (int)want;
+  const long need = ((long)p.Ncap * 21 / 20) / p.scan_lines;
+  const long fixed = (long)p.scan_regions * (p.edges_per_region + 1) * 4 + (long)p.scan_regions * 4 + 16 + 1024 /* s_spill */;
+  long cap = kRingSmemCap;
+  for (int k = 4; k >= 1; --k) {
+    long ck = ((228L * 1024) / k - 2048 - fixed) * 4 / 97;   // 24 B per point + 2 bitmap bits per point = 24.25 B
+    ck = ck / 32 * 32;
+    if (ck > kRingSmemCap) ck = kRingSmemCap;
+    if (ck >= need || k == 1) { cap = ck; break; }
+  }
+  if (cap < 1024) cap = 1024;
+  return (int)cap;
 }
 
 int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
