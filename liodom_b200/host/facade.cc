@@ -546,6 +546,7 @@ struct liodom_host_options {
   int lidar_type, scan_lines, scan_regions, edges_per_region, prev_frames, mapping;
   int width, height;   // organised clouds (lidar_type 1)
   int lockstep;        // 1: wait for each frame's pose before pushing the next cloud (deterministic)
+  int filter_local_map;
 };
 
 // scans: concatenated float32 x,y,z,intensity; npts[nframes]. poses_out: nframes x 16 (row-major).
@@ -560,6 +561,7 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
   nh.setParam("lidar_type", opt->lidar_type); nh.setParam("scan_lines", opt->scan_lines);
   nh.setParam("scan_regions", opt->scan_regions); nh.setParam("edges_per_region", opt->edges_per_region);
   nh.setParam("prev_frames", opt->prev_frames); nh.setParam("mapping", opt->mapping != 0);
+  nh.setParam("filter_local_map", opt->filter_local_map != 0);
   Params::getInstance()->readParams(nh);
   Stats* stats = Stats::getInstance();
   stats->clear();

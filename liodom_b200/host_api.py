@@ -14,7 +14,7 @@ class HostOptions(ctypes.Structure):
     _fields_ = [("min_range", ctypes.c_double), ("max_range", ctypes.c_double), ("lidar_type", ctypes.c_int),
                 ("scan_lines", ctypes.c_int), ("scan_regions", ctypes.c_int), ("edges_per_region", ctypes.c_int),
                 ("prev_frames", ctypes.c_int), ("mapping", ctypes.c_int), ("width", ctypes.c_int), ("height", ctypes.c_int),
-                ("lockstep", ctypes.c_int)]
+                ("lockstep", ctypes.c_int), ("filter_local_map", ctypes.c_int)]
 
 
 def load():
@@ -30,7 +30,7 @@ def run_sequence(scans, results_dir="", lockstep=True, width=0, height=0, **kw):
     lib = load()
     o = HostOptions(kw.get("min_range", 3.0), kw.get("max_range", 75.0), kw.get("lidar_type", 0), kw.get("scan_lines", 64),
                     kw.get("scan_regions", 8), kw.get("edges_per_region", 10), kw.get("prev_frames", 5), int(kw.get("mapping", 0)),
-                    width, height, 1 if lockstep else 0)
+                    width, height, 1 if lockstep else 0, int(kw.get("filter_local_map", 0)))
     npts = np.array([len(s) for s in scans], np.int32)
     pts = np.ascontiguousarray(np.concatenate(scans)[:, :4], dtype=np.float32)
     poses = np.zeros((len(scans), 16))
@@ -52,7 +52,7 @@ def run_sequence_msgs(blobs, widths, heights, point_step, fields, row_pad=0, res
     lib.liodom_host_run_sequence_msgs.restype = ctypes.c_int
     o = HostOptions(kw.get("min_range", 3.0), kw.get("max_range", 75.0), kw.get("lidar_type", 0), kw.get("scan_lines", 64),
                     kw.get("scan_regions", 8), kw.get("edges_per_region", 10), kw.get("prev_frames", 5), int(kw.get("mapping", 0)),
-                    0, 0, 1 if lockstep else 0)
+                    0, 0, 1 if lockstep else 0, int(kw.get("filter_local_map", 0)))
     data = np.ascontiguousarray(np.concatenate([np.asarray(b, np.uint8).ravel() for b in blobs]))
     w = np.array(widths, np.int32)
     h = np.array(heights, np.int32)

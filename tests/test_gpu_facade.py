@@ -47,3 +47,28 @@ def test_facade_free_running_pipeline(cuda_lib):
     b, _, pb = host_api.run_sequence(scans, lockstep=False, prev_frames=5)
     assert pa == pb == len(scans)
     assert np.array_equal(a, b)
+
+
+def test_facade_filter_local_map(cuda_lib):
+    """The `filter_local_map` ROS parameter reaches the device through Params -> LaserOdometer (VoxelGrid of the
+    full window as the kNN target, src/laser_odometry.cc:286-292): façade poses equal the C-ABI's and follow the oracle."""
+    scans, _ = get_sequence("hdl64_small", 1002, 9)
+    poses, nfeats, produced = host_api.run_sequence(scans, prev_frames=4, filter_local_map=1)
+    assert produced == len(scans)
+    ctx = api.Context(prev_frames=4, filter_local_map=1, max_points=32768)
+    ref = api.Context(prev_frames=4, filter_local_map=0, max_points=32768)
+    op = oracle.make_params(prev_frames=4, filter_local_map=1)
+    oposes, _, _ = oracle.run_sequence(op, scans)
+    differs = False
+    for f, s in enumerate(scans):
+        ctx.scan_batch([s])
+        p, _ = ctx.results()
+        ref.scan_batch([s])
+        q, _ = ref.results()
+        assert np.array_equal(p[0], poses[f])
+        differs |= not np.array_equal(p[0], q[0])
+        dt, dr = pose_err(poses[f], oposes[f])
+        assert dt < 1e-3 and dr < 1e-4
+    assert differs      # the filter changed the registration once the window was full
+    ctx.close()
+    ref.close()
