@@ -53,6 +53,23 @@ def main():
     # 3. a free-running 6-frame trajectory (poses only)
     poses, _, _ = oracle.run_sequence(oracle.make_params(prev_frames=5), scans)
     np.savez_compressed(os.path.join(HERE, "trajectory_hdl64_small.npz"), seed=seed, poses=poses)
+    # 4. the steps either side of the path: window filter, IMU override, odometry message, PointCloud2 decode
+    K = 4
+    pf = oracle.make_params(prev_frames=K, filter_local_map=1)
+    poses_f, _, _ = oracle.run_sequence(pf, scans)
+    window4 = np.concatenate([oracle.transform(edges[k], rel[k]) for k in range(K)])
+    filt = oracle.voxelgrid(window4, 0.4)
+    l2b = np.eye(4)
+    l2b[:3, :3] = Rotation.from_euler("ZYX", [0.3, -0.015, 0.01]).as_matrix()
+    l2b[:3, 3] = [0.2, 0.1, -1.5]
+    imu_q = Rotation.from_euler("ZYX", [0.7, 0.02, -0.03]).as_quat()
+    over = oracle.imu_override(rel[3], imu_q, l2b)
+    odo = oracle.publish_odom(rel[3], rel[2], l2b, 0.1)
+    rng = np.random.default_rng(seed)
+    blob = rng.integers(0, 256, 22 * 64, dtype=np.uint8)
+    dec = oracle.decode_cloud2(blob, 16, 4, 22, 16 * 22, 0, 4, 8, 12)
+    np.savez_compressed(os.path.join(HERE, "extras_hdl64_small.npz"), seed=seed, poses_filtered=poses_f, filtered_window=filt,
+                        l2b=l2b, imu_q=imu_q, pose3=rel[3], pose2=rel[2], imu_override=over, odometry=odo, blob=blob, decoded=dec)
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -114,3 +114,44 @@ def test_gpu_use_imu_matches_oracle(cuda_lib):
         sizes = (sizes + [len(edges)])[-5:]
     # the override must actually have changed something relative to use_imu=0
     ctx.close()
+
+
+def _extras():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "extras_hdl64_small.npz"))
+
+
+def test_golden_extras_pin_the_oracle():
+    """Committed vectors (tests/golden/make_golden.py) for the steps either side of the path: window filter,
+    IMU override, odometry message, PointCloud2 decode."""
+    g = _extras()
+    scans, gt = get_sequence("hdl64_small", int(g["seed"]), 6)
+    op = oracle.make_params()
+    edges = []
+    for s in scans:
+        sp = oracle.split(op, s)
+        edges.append(oracle.extract(op, sp["rings"], sp["offsets"])["edges"])
+    rel = [np.linalg.inv(gt[0]) @ p for p in gt]
+    window = np.concatenate([oracle.transform(edges[k], rel[k]) for k in range(4)])
+    assert np.array_equal(oracle.voxelgrid(window, 0.4).view(np.uint32), g["filtered_window"].view(np.uint32))
+    poses, _, _ = oracle.run_sequence(oracle.make_params(prev_frames=4, filter_local_map=1), scans)
+    assert np.allclose(poses, g["poses_filtered"], rtol=0, atol=1e-12)
+    assert np.allclose(oracle.imu_override(g["pose3"], g["imu_q"], g["l2b"]), g["imu_override"], rtol=0, atol=1e-14)
+    assert np.allclose(oracle.publish_odom(g["pose3"], g["pose2"], g["l2b"], 0.1), g["odometry"], rtol=0, atol=1e-13)
+    dec = oracle.decode_cloud2(g["blob"], 16, 4, 22, 16 * 22, 0, 4, 8, 12)
+    assert np.array_equal(dec.view(np.uint32), g["decoded"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden_extras(cuda_lib):
+    """The CUDA path against the committed vectors: filtered-window trajectory and the decoded cloud's edges."""
+    from liodom_b200 import api
+    g = _extras()
+    scans, _ = get_sequence("hdl64_small", int(g["seed"]), 6)
+    ctx = api.Context(prev_frames=4, filter_local_map=1, max_points=32768)
+    for f, s in enumerate(scans):
+        ctx.scan_batch([s])
+        p, _ = ctx.results()
+        dt, dr = pose_err(p[0], g["poses_filtered"][f])
+        assert dt < 1e-3 and dr < 1e-4, (f, dt, dr)
+    ctx.close()
