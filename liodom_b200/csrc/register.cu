@@ -698,32 +698,33 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
 #undef SUB
 #undef DIV
 
-// 4 threads per edge while the launch would otherwise leave most of the 148 SMs idle
-// (LIODOM_ASSOC_GROUP=1|4 forces a variant; used by the parity tests to cover both.)
-static bool assoc_use_groups(long long edges_in_flight) {
-  if (const char* e = getenv("LIODOM_ASSOC_GROUP")) { if (e[0] == '1') return false; if (e[0] == '4') return true; }
-  return edges_in_flight <= 12 * 5632;
+// Threads per edge: 1 for large batches (least total work); 4, 8 or 16 while the launch would otherwise leave most
+// of the 148 SMs idle (shorter per-edge chains; measured per lane count).  LIODOM_ASSOC_GROUP=1|4|8|16 forces a
+// variant (the parity tests cover all four).
+static int assoc_group_size(long long edges_in_flight) {
+  if (const char* e = getenv("LIODOM_ASSOC_GROUP")) { const int v = atoi(e); if (v == 1 || v == 4 || v == 8 || v == 16) return v; }
+  if (edges_in_flight <= 5632) return 16;
+  if (edges_in_flight <= 2 * 5632) return 8;
+  return edges_in_flight <= 12 * 5632 ? 4 : 1;
+}
+
+static void launch_associate_any(const DevBuffers& d, cudaStream_t s, int lane0, int nlanes, int edges_per_lane, int outer_it, int force,
+                                 const double* pose_override, int rank, int world) {
+  const int G = assoc_group_size((long long)edges_per_lane * nlanes);
+  const dim3 g((unsigned)(((long long)edges_per_lane * G + kAssocThreads - 1) / kAssocThreads), nlanes);
+  if (G == 16) k_associate<16><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+  else if (G == 8) k_associate<8><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+  else if (G == 4) k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+  else k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
 }
 
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
-  if (assoc_use_groups((long long)d.p.Ecap * lr.nlanes)) {
-    const dim3 g((d.p.Ecap * 4 + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
-    k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
-  } else {
-    const dim3 g((d.p.Ecap + kAssocThreads - 1) / kAssocThreads, lr.nlanes);
-    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lr.lane0, outer_it, force ? 1 : 0, pose_override, 0, 1);
-  }
+  launch_associate_any(d, s, lr.lane0, lr.nlanes, d.p.Ecap, outer_it, force ? 1 : 0, pose_override, 0, 1);
   return 1;
 }
 int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world) {
   const int share = ((d.p.Ecap + world - 1) / world + 31) & ~31;
-  if (assoc_use_groups(share)) {
-    const dim3 g((share * 4 + kAssocThreads - 1) / kAssocThreads, 1);
-    k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
-  } else {
-    const dim3 g((share + kAssocThreads - 1) / kAssocThreads, 1);
-    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane, outer_it, 0, nullptr, rank, world);
-  }
+  launch_associate_any(d, s, lane, 1, share, outer_it, 0, nullptr, rank, world);
   return 1;
 }
 

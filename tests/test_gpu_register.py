@@ -81,9 +81,9 @@ def _teacher_forced_associate(ctx, edges_seq, gt, K):
     return nchecked
 
 
-@pytest.mark.parametrize("group", ["1", "4"])
+@pytest.mark.parametrize("group", ["1", "4", "8", "16"])
 def test_associate_teacher_forced_c1(cuda_lib, group, monkeypatch):
-    """Both kernel variants (1 or 4 threads per edge; picked by the number of edges in flight)."""
+    """Every kernel variant (1, 4, 8 or 16 threads per edge; picked by the number of edges in flight)."""
     monkeypatch.setenv("LIODOM_ASSOC_GROUP", group)
     scans, gt = get_sequence("hdl64", 1000, 5)
     op = oracle.make_params(prev_frames=15)
@@ -219,7 +219,7 @@ def _run_teacher_forced(sensor, seed, nframes, okw, gkw, max_points, traj=0, wid
     return worst
 
 
-@pytest.mark.parametrize("group", ["1", "4"])
+@pytest.mark.parametrize("group", ["1", "4", "16"])
 def test_register_teacher_forced_c1(cuda_lib, group, monkeypatch):
     monkeypatch.setenv("LIODOM_ASSOC_GROUP", group)
     w = _run_teacher_forced("hdl64", 1000, 20, dict(prev_frames=15), dict(prev_frames=15), 131072)
