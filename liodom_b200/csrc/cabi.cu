@@ -229,6 +229,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.lin, B * p.Mcap));
   CKC(dalloc(c, &d.htab, B * p.Hcap));
   CKC(dalloc(c, &d.bloom, B * p.Bwords));
+  CKC(dalloc(c, &d.owner_list, B * p.Mcap));
   CKC(dalloc(c, &d.pt_slot, B * p.Mcap));
   CKC(dalloc(c, &d.pt_rank, B * p.Mcap));
   CKC(dalloc(c, &d.perm, B * p.Ecap));

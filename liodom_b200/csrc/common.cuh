@@ -74,7 +74,7 @@ struct WinState {
   unsigned gen;           // hash generation of the current build
   int hash_points;        // points inserted in the current hash build
   int bump;               // bucket allocator
-  int pad;
+  int n_owners;           // cells created by the current hash build (entries of owner_list)
   // logical view of the window (oldest frame first), refreshed whenever the window changes:
   int view_prefix[kMaxSlots + 1];   // first logical index of frame k
   int view_slab[kMaxSlots];         // slab holding frame k
@@ -147,6 +147,7 @@ struct DevBuffers {
   float4* lin;             // [B][Mcap] the same points in logical (window) order
   HashEntry* htab;         // [B][Hcap]
   unsigned* bloom;         // [B][Bwords] occupancy filter of the hash cells: word = hash(ix >> 5, iy, iz), bit = ix & 31
+  unsigned* owner_list;    // [B][Mcap] hash slots of the cells created by the current build
   unsigned* pt_slot;       // [B][Mcap]
   unsigned* pt_rank;       // [B][Mcap]
   int* perm;               // [B][Ecap] Morton-ordered edge indices (thread -> edge) of k_associate

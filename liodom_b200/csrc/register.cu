@@ -24,6 +24,7 @@ __device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
   ws.view_prefix[ws.nframes] = acc;
   ws.gen = ws.gen + 1u;
   ws.bump = 0;
+  ws.n_owners = 0;
   ws.hash_points = ws.total + (d.p.mapping ? ws.n_received : 0);
   // computeLocalMap (src/laser_odometry.cc:286): filter iff the window is full and mapping is off;
   // launch_window_filter then replaces the target (and hash_points) before the hash is built.
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
       }
       slot = (slot + 1) & mask;
     }
-    if (owner) {   // first point of the cell: publish it in the occupancy filter read by k_associate
+    if (owner) {   // first point of the cell: list it for k_hash_alloc and publish it in the occupancy filter read by k_associate
+      d.owner_list[(size_t)lane_b * d.p.Mcap + atomicAdd(&d.wstate[lane_b].n_owners, 1)] = slot;
       const int ix = cell_of(pt.x);
       atomicOr(d.bloom + (size_t)lane_b * d.p.Bwords + bloom_word_index(ix >> 5, cell_of(pt.y), cell_of(pt.z), (unsigned)d.p.Bwords - 1u), 1u << (ix & 31));
     }
@@ -84,17 +86,26 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
   }
 }
 
+// Bucket allocation: one thread per CELL (the creators appended their slots to owner_list during the insert),
+// a warp-wide prefix of the counts and one bump per warp.
 __global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
   WinState& ws = d.wstate[lane_b];
-  const int npts = ws.hash_points;
+  const int ncell = ws.n_owners, ln = threadIdx.x & 31;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
-    const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
-    if (ps != 0xffffffffu && (ps & 0x80000000u)) {
-      const unsigned slot = ps & 0x7fffffffu;
-      tab[slot].start = (unsigned)atomicAdd(&ws.bump, (int)(tab[slot].cnt & ((1u << kCntBits) - 1u)));
-    }
+  const unsigned* owners = d.owner_list + (size_t)lane_b * d.p.Mcap;
+  const int stride = gridDim.x * blockDim.x;
+  for (int j0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); j0 < ncell; j0 += stride) {   // warp-uniform trip count
+    const int j = j0 + ln;
+    unsigned slot = 0, cnt = 0;
+    if (j < ncell) { slot = owners[j]; cnt = tab[slot].cnt & ((1u << kCntBits) - 1u); }
+    unsigned incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += t; }
+    unsigned base = 0;
+    if (ln == 31) base = (unsigned)atomicAdd(&ws.bump, (int)incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (j < ncell) tab[slot].start = base + incl - cnt;
   }
 }
 
