@@ -233,6 +233,7 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.pt_slot, B * p.Mcap));
   CKC(dalloc(c, &d.pt_rank, B * p.Mcap));
   CKC(dalloc(c, &d.perm, B * p.Ecap));
+  CKC(dalloc(c, &d.knn_out, B * p.Ecap * 5));
   CKC(dalloc(c, &d.blocks, B * p.Ecap * 10));
   CKC(dalloc(c, &d.knn_idx, B * p.Ecap * 5));
   CKC(dalloc(c, &d.knn_d2, B * p.Ecap * 5));

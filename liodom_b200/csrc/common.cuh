@@ -151,6 +151,7 @@ struct DevBuffers {
   unsigned* pt_slot;       // [B][Mcap]
   unsigned* pt_rank;       // [B][Mcap]
   int* perm;               // [B][Ecap] Morton-ordered edge indices (thread -> edge) of k_associate
+  int* knn_out;            // [B][Ecap][5] neighbours found by k_associate (logical indices, -1: fewer than five within 1 m)
   float* blocks;           // [B][Ecap][10]
   int* knn_idx;            // [B][Ecap][5] (debug) or null
   float* knn_d2;           // [B][Ecap][5]

@@ -508,6 +508,46 @@ __device__ __forceinline__ void knn_scan_row(const HashEntry* __restrict__ tab, 
   }
 }
 
+// Line gate and residual block of one edge (src/laser_odometry.cc:324-361): centroid and scatter of the five
+// neighbours in double, eigenvalues, lambda2 > 3 lambda1, block {c, a, b, valid}.  nn_idx[0] < 0: fewer than five
+// neighbours within 1 m.  Returns true when the edge yields a residual block.
+__device__ __forceinline__ bool line_gate(const DevBuffers& d, int lane_b, int e, const float4& c, const int* nn_idx) {
+  const DevParams& p = d.p;
+  uint8_t gt = 0;
+  double ev[3] = {0.0, 0.0, 0.0};
+  float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+  if (nn_idx[0] >= 0) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
+    gt |= 1;
+    const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
+    float4 nn[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) nn[r] = lin[nn_idx[r]];
+    // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
+    double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) { mx = ADD(mx, (double)nn[r].x); my = ADD(my, (double)nn[r].y); mz = ADD(mz, (double)nn[r].z); }
+    mx = DIV(mx, 5.0); my = DIV(my, 5.0); mz = DIV(mz, 5.0);
+    double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const double dx = SUB((double)nn[r].x, mx), dy = SUB((double)nn[r].y, my), dz = SUB((double)nn[r].z, mz);
+      c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
+      c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
+    }
+    sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
+    if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
+  }
+  float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
+  blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;
+  blk[6] = b.x; blk[7] = b.y; blk[8] = b.z; blk[9] = (gt & 2) ? 1.0f : 0.0f;
+  if (d.gate) {
+    const size_t o = (size_t)lane_b * p.Ecap + e;
+    d.gate[o] = gt;
+    d.eig[o * 3] = ev[0]; d.eig[o * 3 + 1] = ev[1]; d.eig[o * 3 + 2] = ev[2];
+  }
+  return (gt & 2) != 0;
+}
+
 constexpr int kAssocThreads = 64;
 
 // Visit order of the 27 cells of a cube: per axis 0 = own cell, 1 = the neighbour behind the nearer
@@ -544,7 +584,6 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
   const int ln = threadIdx.x & 31;
   const int gl = ln & (G - 1);                                   // lane inside the edge's group
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (ln & ~(G - 1)));
-  bool match = false;
   if (active && (t - ln / G) < E) {   // warp-uniform: the fallback search below is cooperative
     const WinState& ws = d.wstate[lane_b];
     const double* T = pose_override ? pose_override : os.odom;
@@ -659,50 +698,59 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
         }
       }
     }
-    uint8_t gt = 0;
-    double ev[3] = {0.0, 0.0, 0.0};
-    float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-    if (mine && gl == 0 && k.k[4] != kEmptyCand) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
-      gt |= 1;
-      const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
-      float4 nn[5];
-#pragma unroll
-      for (int r = 0; r < 5; ++r) nn[r] = lin[(unsigned)k.k[r]];
-      // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
-      double mx = 0.0, my = 0.0, mz = 0.0;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) { mx = ADD(mx, (double)nn[r].x); my = ADD(my, (double)nn[r].y); mz = ADD(mz, (double)nn[r].z); }
-      mx = DIV(mx, 5.0); my = DIV(my, 5.0); mz = DIV(mz, 5.0);
-      double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const double dx = SUB((double)nn[r].x, mx), dy = SUB((double)nn[r].y, my), dz = SUB((double)nn[r].z, mz);
-        c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
-        c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
-      }
-      sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
-      if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
-    }
+    // G == 1 (large batches): the search ends here and the five neighbours go to k_line_gate, so that the search
+    // kernel's register budget is not shared with the FP64 eigen-solver (no spills to speak of: -13 % at 128 lanes).
+    // G > 1 (few edges in flight): gate in place — one launch less matters more there.
+    bool match = false;
     if (mine && gl == 0) {
-      float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
-      blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;
-      blk[6] = b.x; blk[7] = b.y; blk[8] = b.z; blk[9] = (gt & 2) ? 1.0f : 0.0f;
-    }
-    match = (gt & 2) != 0;
-    if (mine && gl == 0 && d.gate) {
-      const size_t o = (size_t)lane_b * p.Ecap + e;
-      d.gate[o] = gt;
-      for (int r = 0; r < 5; ++r) {
-        d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
-        d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
+      int nn_idx[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) nn_idx[r] = k.k[4] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+      if (G == 1) {
+        int* nn_out = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) nn_out[r] = nn_idx[r];
+      } else {
+        match = line_gate(d, lane_b, e, c, nn_idx);
       }
-      d.eig[o * 3] = ev[0]; d.eig[o * 3 + 1] = ev[1]; d.eig[o * 3 + 2] = ev[2];
-      d.q_world[o] = make_float4(qx, qy, qz, c.w);
+      if (d.gate) {
+        const size_t o = (size_t)lane_b * p.Ecap + e;
+        for (int r = 0; r < 5; ++r) {
+          d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+          d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
+        }
+        d.q_world[o] = make_float4(qx, qy, qz, c.w);
+      }
     }
+    if (G != 1) {
+      const int nm = __popc(__ballot_sync(0xffffffffu, match));
+      if (ln == 0 && nm) atomicAdd(&d.diag[lane_b].n_matches[outer_it], nm);
+    }
+  }
+  if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
+}
+
+// The gate of every edge after a G == 1 search, one thread per edge in edge order (the edge-sharded mode: this
+// rank's Morton positions).
+__global__ void __launch_bounds__(128) k_line_gate(DevBuffers d, int lane0, int outer_it, int force, int shard_rank, int shard_world) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y;
+  const OdomState& os = d.ostate[lane_b];
+  const bool active = force || os.init;
+  const int share = shard_world > 1 ? (((os.n_edges + shard_world - 1) / shard_world + 31) & ~31) : 0;
+  const int E = shard_world > 1 ? min(os.n_edges, (shard_rank + 1) * share) : os.n_edges;
+  const int t = shard_rank * share + blockIdx.x * blockDim.x + threadIdx.x;
+  bool match = false;
+  if (active && t < E) {
+    const int e = shard_world > 1 ? d.perm[(size_t)lane_b * p.Ecap + t] : t;   // unsharded: edge order (coalesced)
+    const int* nn_in = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+    int nn_idx[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) nn_idx[r] = nn_in[r];
+    match = line_gate(d, lane_b, e, d.edges[(size_t)lane_b * p.Ecap + e], nn_idx);
   }
   const int nm = __popc(__ballot_sync(0xffffffffu, match));
   if ((threadIdx.x & 31) == 0 && nm) atomicAdd(&d.diag[lane_b].n_matches[outer_it], nm);
-  if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
 }
 #undef MUL
 #undef ADD
@@ -726,17 +774,20 @@ static void launch_associate_any(const DevBuffers& d, cudaStream_t s, int lane0,
   if (G == 16) k_associate<16><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
   else if (G == 8) k_associate<8><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
   else if (G == 4) k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
-  else k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+  else {
+    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+    k_line_gate<<<dim3((edges_per_lane + 127) / 128, nlanes), 128, 0, s>>>(d, lane0, outer_it, force, rank, world);
+  }
 }
 
 int launch_associate(const DevBuffers& d, cudaStream_t s, LaneRange lr, int outer_it, bool force, const double* pose_override) {
   launch_associate_any(d, s, lr.lane0, lr.nlanes, d.p.Ecap, outer_it, force ? 1 : 0, pose_override, 0, 1);
-  return 1;
+  return 2;
 }
 int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world) {
   const int share = ((d.p.Ecap + world - 1) / world + 31) & ~31;
   launch_associate_any(d, s, lane, 1, share, outer_it, 0, nullptr, rank, world);
-  return 1;
+  return 2;
 }
 
 // ---------------------------------------------------------------------------------------
