@@ -12,37 +12,35 @@ namespace liodom {
 
 class Params {
  public:
-  double min_range_;
-  double max_range_;
-  int lidar_type_;
-  int scan_lines_;
-  int scan_regions_;
-  int edges_per_region_;
-  size_t min_points_per_scan_;
-  size_t local_map_size_;
-  bool save_results_;
-  std::string results_dir_;
-  std::string fixed_frame_;
-  std::string base_frame_;
-  std::string laser_frame_;
-  bool use_imu_;
-  bool filter_local_map_;
-  bool mapping_;
-  bool publish_tf_;
-
+  // --- process-wide instance (the reference's singleton access, include/liodom/params.h:54-56) ---
   static Params* getInstance();
-  Params(Params const&) = delete;
-  void operator=(Params const&) = delete;
-
   void readParams(const NodeHandle& nh);
 
- private:
-  static Params* pinstance_;
-  static std::mutex params_mutex_;
+  // --- sensor and extraction (src/params.cc:40-66) ---
+  double min_range_, max_range_;          // XY range gate of isValidPoint [m]
+  int lidar_type_;                        // 0 Velodyne (ring from elevation), 1 Ouster (ring = row)
+  int scan_lines_, scan_regions_, edges_per_region_;
+  size_t min_points_per_scan_;            // derived: scan_regions * edges_per_region + 10
+
+  // --- registration (src/params.cc:68-72, :96-104) ---
+  size_t local_map_size_;                 // "prev_frames"
+  bool use_imu_, filter_local_map_, mapping_;
+
+  // --- outputs (src/params.cc:74-94, :106-108) ---
+  bool save_results_, publish_tf_;
+  std::string results_dir_;
+  std::string fixed_frame_, base_frame_, laser_frame_;
+
+  Params(Params const&) = delete;
+  void operator=(Params const&) = delete;
 
  protected:
   Params() { readParams(NodeHandle()); }
   ~Params() {}
+
+ private:
+  static Params* instance_;
+  static std::mutex instance_mutex_;
 };
 
 }  // namespace liodom

@@ -14,38 +14,35 @@ namespace liodom {
 class SharedData {
  public:
   static SharedData* getInstance();
-  SharedData(SharedData const&) = delete;
-  void operator=(SharedData const&) = delete;
 
+  // ROS callback thread -> extractor thread: scans by pointer, FIFO (src/shared_data.cc:37-62)
   void pushPointCloud(const PointCloud::Ptr& pc_in, const Header& header);
   bool popPointCloud(PointCloud::Ptr& pc_out, Header& header);
-
+  // extractor thread -> odometry thread: edge clouds by pointer, FIFO (:64-89)
   void pushFeatures(const PointCloud::Ptr& feat_in, Header& header);
   bool popFeatures(PointCloud::Ptr& feat_out, Header& header);
-
+  // mapping process -> odometry: latest local map, deep-copied both ways (:91-105)
   void setLocalMap(const PointCloud::Ptr& map_in);
   void getLocalMap(PointCloud::Ptr& map_out);
-
+  // IMU callback -> odometry: latest orientation (:107-117)
   void setLastIMUOri(Quaterniond& imu_ori);
   void getLastIMUOri(Quaterniond& imu_ori);
 
- private:
-  static SharedData* pinstance_;
-  static std::mutex sdata_mutex_;
-  std::mutex pc_mutex_;
-  std::queue<PointCloud::Ptr> pc_buf_;
-  std::queue<Header> pc_header_;
-  std::mutex feat_mutex_;
-  std::queue<PointCloud::Ptr> feat_buf_;
-  std::queue<Header> feat_header_;
-  std::mutex map_mutex_;
-  PointCloud::Ptr local_map_;
-  std::mutex imu_mutex_;
-  Quaterniond last_IMU_ori_;
+  SharedData(SharedData const&) = delete;
+  void operator=(SharedData const&) = delete;
 
  protected:
   SharedData() : local_map_(new PointCloud) {}
   ~SharedData() {}
+
+ private:
+  template <typename T> struct Fifo { std::mutex m; std::queue<T> items; std::queue<Header> headers; };
+  static SharedData* instance_;
+  static std::mutex instance_mutex_;
+  Fifo<PointCloud::Ptr> scans_, feats_;
+  std::mutex map_mutex_, imu_mutex_;
+  PointCloud::Ptr local_map_;
+  Quaterniond last_imu_;
 };
 
 }  // namespace liodom

@@ -17,35 +17,37 @@ namespace liodom {
 class Stats {
  public:
   static Stats* getInstance();
-  Stats(Stats const&) = delete;
-  void operator=(Stats const&) = delete;
 
+  // per-frame records (src/stats.cc:36-71)
   void addPose(const Matrix4d& pose);
+  void addNumOfFeats(const size_t& nfeats);
   void addFeatureExtractionTime(const Clock::time_point& start, const Clock::time_point& end);
   void addLaserOdometryTime(const Clock::time_point& start, const Clock::time_point& end);
-  void addNumOfFeats(const size_t& nfeats);
+  // whole-frame latency: startFrame in lidarClb, stopFrame when the pose is out (FIFO of start times)
   void startFrame(const Clock::time_point& start);
   void stopFrame(const Clock::time_point& stop);
+  // the five text files (src/stats.cc:73-132)
   void writeResults(const std::string& dir);
 
   /* additions for the array-driven harness (not in the reference) */
   void clear();
   const std::vector<Matrix4d>& poses() const { return poses_; }
 
- private:
-  static Stats* pinstance_;
-  static std::mutex sdata_mutex_;
-  std::vector<Matrix4d> poses_;
-  std::vector<double> feat_extr_;
-  std::vector<double> laser_odom_;
-  std::vector<size_t> num_of_features_;
-  std::mutex frame_mutex_;
-  std::queue<Clock::time_point> start_times_;
-  std::vector<double> frame_times_;
+  Stats(Stats const&) = delete;
+  void operator=(Stats const&) = delete;
 
  protected:
   Stats() {}
   ~Stats() {}
+
+ private:
+  static Stats* instance_;
+  static std::mutex instance_mutex_;
+  std::mutex frame_mutex_;                       // guards pending_starts_ / frame_ms_
+  std::queue<Clock::time_point> pending_starts_;
+  std::vector<Matrix4d> poses_;
+  std::vector<size_t> nfeats_;
+  std::vector<double> extract_ms_, odom_ms_, frame_ms_;   // whole milliseconds, as the reference truncates them
 };
 
 }  // namespace liodom

@@ -25,13 +25,13 @@ static bool verbose() { static const bool v = std::getenv("LIODOM_VERBOSE") != n
 // ---------------------------------------------------------------------------------------------
 // Params (src/params.cc:24-110)
 // ---------------------------------------------------------------------------------------------
-Params* Params::pinstance_{nullptr};
-std::mutex Params::params_mutex_;
+Params* Params::instance_{nullptr};
+std::mutex Params::instance_mutex_;
 
 Params* Params::getInstance() {
-  std::lock_guard<std::mutex> lock(params_mutex_);
-  if (pinstance_ == nullptr) pinstance_ = new Params();
-  return pinstance_;
+  std::lock_guard<std::mutex> lock(instance_mutex_);
+  if (!instance_) instance_ = new Params();
+  return instance_;
 }
 
 void Params::readParams(const NodeHandle& nh) {
@@ -61,36 +61,32 @@ void Params::readParams(const NodeHandle& nh) {
 // ---------------------------------------------------------------------------------------------
 // SharedData (src/shared_data.cc:24-117)
 // ---------------------------------------------------------------------------------------------
-SharedData* SharedData::pinstance_{nullptr};
-std::mutex SharedData::sdata_mutex_;
+SharedData* SharedData::instance_{nullptr};
+std::mutex SharedData::instance_mutex_;
 
 SharedData* SharedData::getInstance() {
-  std::lock_guard<std::mutex> lock(sdata_mutex_);
-  if (pinstance_ == nullptr) pinstance_ = new SharedData();
-  return pinstance_;
+  std::lock_guard<std::mutex> lock(instance_mutex_);
+  if (!instance_) instance_ = new SharedData();
+  return instance_;
 }
-void SharedData::pushPointCloud(const PointCloud::Ptr& pc_in, const Header& header) {
-  std::lock_guard<std::mutex> lock(pc_mutex_);
-  pc_buf_.push(pc_in); pc_header_.push(header);
+// Both queues share one shape: the cloud pointer and its header travel together, nothing is copied.
+template <typename F>
+static void fifo_push(F& q, const PointCloud::Ptr& cloud, const Header& header) {
+  std::lock_guard<std::mutex> lock(q.m);
+  q.items.push(cloud); q.headers.push(header);
 }
-bool SharedData::popPointCloud(PointCloud::Ptr& pc_out, Header& header) {
-  std::lock_guard<std::mutex> lock(pc_mutex_);
-  if (pc_buf_.empty()) return false;
-  pc_out = pc_buf_.front(); pc_buf_.pop();
-  header = pc_header_.front(); pc_header_.pop();
+template <typename F>
+static bool fifo_pop(F& q, PointCloud::Ptr& cloud, Header& header) {
+  std::lock_guard<std::mutex> lock(q.m);
+  if (q.items.empty()) return false;
+  cloud = q.items.front(); q.items.pop();
+  header = q.headers.front(); q.headers.pop();
   return true;
 }
-void SharedData::pushFeatures(const PointCloud::Ptr& feat_in, Header& header) {
-  std::lock_guard<std::mutex> lock(feat_mutex_);
-  feat_buf_.push(feat_in); feat_header_.push(header);
-}
-bool SharedData::popFeatures(PointCloud::Ptr& feat_out, Header& header) {
-  std::lock_guard<std::mutex> lock(feat_mutex_);
-  if (feat_buf_.empty()) return false;
-  feat_out = feat_buf_.front(); feat_buf_.pop();
-  header = feat_header_.front(); feat_header_.pop();
-  return true;
-}
+void SharedData::pushPointCloud(const PointCloud::Ptr& pc_in, const Header& header) { fifo_push(scans_, pc_in, header); }
+bool SharedData::popPointCloud(PointCloud::Ptr& pc_out, Header& header) { return fifo_pop(scans_, pc_out, header); }
+void SharedData::pushFeatures(const PointCloud::Ptr& feat_in, Header& header) { fifo_push(feats_, feat_in, header); }
+bool SharedData::popFeatures(PointCloud::Ptr& feat_out, Header& header) { return fifo_pop(feats_, feat_out, header); }
 void SharedData::setLocalMap(const PointCloud::Ptr& map_in) {
   std::lock_guard<std::mutex> lock(map_mutex_);
   *local_map_ = *map_in;   // pcl::copyPointCloud: deep copy
@@ -99,40 +95,40 @@ void SharedData::getLocalMap(PointCloud::Ptr& map_out) {
   std::lock_guard<std::mutex> lock(map_mutex_);
   *map_out = *local_map_;
 }
-void SharedData::setLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); last_IMU_ori_ = imu_ori; }
-void SharedData::getLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); imu_ori = last_IMU_ori_; }
+void SharedData::setLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); last_imu_ = imu_ori; }
+void SharedData::getLastIMUOri(Quaterniond& imu_ori) { std::lock_guard<std::mutex> lock(imu_mutex_); imu_ori = last_imu_; }
 
 // ---------------------------------------------------------------------------------------------
 // Stats (src/stats.cc:24-132)
 // ---------------------------------------------------------------------------------------------
-Stats* Stats::pinstance_{nullptr};
-std::mutex Stats::sdata_mutex_;
+Stats* Stats::instance_{nullptr};
+std::mutex Stats::instance_mutex_;
 
 Stats* Stats::getInstance() {
-  std::lock_guard<std::mutex> lock(sdata_mutex_);
-  if (pinstance_ == nullptr) pinstance_ = new Stats();
-  return pinstance_;
+  std::lock_guard<std::mutex> lock(instance_mutex_);
+  if (!instance_) instance_ = new Stats();
+  return instance_;
 }
 static double whole_ms(const Clock::time_point& a, const Clock::time_point& b) {
   return (double)std::chrono::duration_cast<std::chrono::milliseconds>(b - a).count();
 }
 void Stats::addPose(const Matrix4d& pose) { poses_.push_back(pose); }
-void Stats::addFeatureExtractionTime(const Clock::time_point& start, const Clock::time_point& end) { feat_extr_.push_back(whole_ms(start, end)); }
-void Stats::addLaserOdometryTime(const Clock::time_point& start, const Clock::time_point& end) { laser_odom_.push_back(whole_ms(start, end)); }
-void Stats::addNumOfFeats(const size_t& nfeats) { num_of_features_.push_back(nfeats); }
-void Stats::startFrame(const Clock::time_point& start) { std::lock_guard<std::mutex> lock(frame_mutex_); start_times_.push(start); }
+void Stats::addFeatureExtractionTime(const Clock::time_point& start, const Clock::time_point& end) { extract_ms_.push_back(whole_ms(start, end)); }
+void Stats::addLaserOdometryTime(const Clock::time_point& start, const Clock::time_point& end) { odom_ms_.push_back(whole_ms(start, end)); }
+void Stats::addNumOfFeats(const size_t& nfeats) { nfeats_.push_back(nfeats); }
+void Stats::startFrame(const Clock::time_point& start) { std::lock_guard<std::mutex> lock(frame_mutex_); pending_starts_.push(start); }
 void Stats::stopFrame(const Clock::time_point& stop) {
   std::lock_guard<std::mutex> lock(frame_mutex_);
-  if (!start_times_.empty()) {
-    const Clock::time_point start = start_times_.front();
-    start_times_.pop();
-    frame_times_.push_back(whole_ms(start, stop));
+  if (!pending_starts_.empty()) {
+    const Clock::time_point start = pending_starts_.front();
+    pending_starts_.pop();
+    frame_ms_.push_back(whole_ms(start, stop));
   }
 }
 void Stats::clear() {
   std::lock_guard<std::mutex> lock(frame_mutex_);
-  poses_.clear(); feat_extr_.clear(); laser_odom_.clear(); num_of_features_.clear(); frame_times_.clear();
-  while (!start_times_.empty()) start_times_.pop();
+  poses_.clear(); extract_ms_.clear(); odom_ms_.clear(); nfeats_.clear(); frame_ms_.clear();
+  while (!pending_starts_.empty()) pending_starts_.pop();
 }
 template <typename V> static void write_column(const std::string& path, const V& v) {
   std::ofstream f(path.c_str(), std::ios::out | std::ios::trunc);
@@ -148,10 +144,10 @@ void Stats::writeResults(const std::string& dir) {
           if (i == 2 && j == 3) f << std::endl; else f << " ";
         }
   }
-  write_column(dir + "feat_ext_times.txt", feat_extr_);
-  write_column(dir + "laser_odom_times.txt", laser_odom_);
-  write_column(dir + "nfeats.txt", num_of_features_);
-  write_column(dir + "frame_times.txt", frame_times_);
+  write_column(dir + "feat_ext_times.txt", extract_ms_);
+  write_column(dir + "odom_ms_times.txt", odom_ms_);
+  write_column(dir + "nfeats.txt", nfeats_);
+  write_column(dir + "frame_times.txt", frame_ms_);
 }
 
 // ---------------------------------------------------------------------------------------------
