@@ -145,7 +145,7 @@ void Stats::writeResults(const std::string& dir) {
         }
   }
   write_column(dir + "feat_ext_times.txt", extract_ms_);
-  write_column(dir + "odom_ms_times.txt", odom_ms_);
+  write_column(dir + "laser_odom_times.txt", odom_ms_);
   write_column(dir + "nfeats.txt", nfeats_);
   write_column(dir + "frame_times.txt", frame_ms_);
 }
