@@ -36,8 +36,7 @@
 namespace {
 
 constexpr int kTile = 2048;            // keys per radix-sort block (256 threads x 8)
-constexpr int kLatBits = 10;           // lattice bits per axis inside a coarse cell
-constexpr int kRankShift = 3 * kLatBits;
+constexpr int kMaxLatBits = 10;        // upper bound of the lattice bits per axis inside a coarse cell (MapDev::lat_bits)
 constexpr unsigned long long kEmptyKey = ~0ull;
 
 struct MapState {      // device-resident scalars
@@ -54,6 +53,7 @@ struct MapState {      // device-resident scalars
 struct MapDev {
   double xy, inv_xy, xy_half, zs, inv_z, z_half;
   float inv_leaf;
+  int lat_bits;          // bits per lattice axis of the sort key: ceil(log2(cell size / resolution + 8)); fewer bits = fewer radix passes
   int cap_points, cap_cells, hcap, cap_new;
   float4* pool[2];
   int* cell_count;       // [cap_cells] points per cell (creation order)
@@ -323,18 +323,19 @@ __global__ void __launch_bounds__(kMapThreads) k_map_update(MapDev m, const floa
     const float fz = (float)((double)m.cell_key[cid * 3 + 2] - m.z_half);
     const int lx = lattice(p.x, m.inv_leaf) - (lattice(fx, m.inv_leaf) - 2), ly = lattice(p.y, m.inv_leaf) - (lattice(fy, m.inv_leaf) - 2);
     const int lz = lattice(p.z, m.inv_leaf) - (lattice(fz, m.inv_leaf) - 2);
-    const int lim = 1 << kLatBits;
+    const int lim = 1 << m.lat_bits;
     if (lx < 0 || lx >= lim || ly < 0 || ly >= lim || lz < 0 || lz >= lim) atomicOr(&st.error, 4);
-    m.keys[0][wi] = ((unsigned long long)r << kRankShift) | ((unsigned long long)(lz & (lim - 1)) << (2 * kLatBits)) |
-                    ((unsigned long long)(ly & (lim - 1)) << kLatBits) | (unsigned long long)(lx & (lim - 1));
+    m.keys[0][wi] = ((unsigned long long)r << (3 * m.lat_bits)) | ((unsigned long long)(lz & (lim - 1)) << (2 * m.lat_bits)) |
+                    ((unsigned long long)(ly & (lim - 1)) << m.lat_bits) | (unsigned long long)(lx & (lim - 1));
     m.vals[0][wi] = (unsigned)wi;
   }
   grid.sync();
 
-  // ---- stable LSD radix sort, 8-bit digits; key bits in use: 30 lattice bits + ceil(log2(n_touched)).
+  // ---- stable LSD radix sort, 8-bit digits; key bits in use: 3 * lat_bits lattice bits + ceil(log2(n_touched)).
   // (kEmptyKey = ~0 of dropped points has every processed digit at 255 and no valid key has, so it still sorts last.)
-  int bits = kRankShift;
-  while ((1 << (bits - kRankShift)) < n_touched) ++bits;
+  const int rank_shift = 3 * m.lat_bits;
+  int bits = rank_shift;
+  while ((1 << (bits - rank_shift)) < n_touched) ++bits;
   const int ntiles = (wtot + kTile - 1) / kTile;
   int sb = 0;
   for (int shift = 0; shift < bits; shift += 8) {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(kMapThreads) k_map_update(MapDev m, const floa
   // first group of every rank; new per-cell counts (touched: its groups; untouched: unchanged)
   for (int r = gtid; r <= n_touched; r += gsize) {
     if (r == n_touched) { m.group_first[r] = n_groups; continue; }
-    const unsigned long long target = (unsigned long long)r << kRankShift;
+    const unsigned long long target = (unsigned long long)r << rank_shift;
     int lo = 0, hi = wtot;  // first position with key >= target
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey[mid] < target) lo = mid + 1; else hi = mid; }
     m.group_first[r] = lo < wtot ? m.head[lo] : n_groups;
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kMapThreads) k_map_update(MapDev m, const floa
       ++cnt;
     }
     const float fc = (float)cnt;
-    const int r = (int)(k >> kRankShift);
+    const int r = (int)(k >> rank_shift);
     const int g = m.head[wi];   // exclusive scan of the head flags = global group index
     const int cid = m.touched_list[r];
     m.pool[cur ^ 1][m.cell_newoff[cid] + (g - m.group_first[r])] = make_float4(__fdiv_rn(sx, fc), __fdiv_rn(sy, fc), __fdiv_rn(sz, fc), __fdiv_rn(si, fc));
@@ -571,7 +572,7 @@ int liodom_map_create(double voxel_xysize, double voxel_zsize, double resolution
   if (voxel_xysize < 1.0 || voxel_zsize < 1.0)   // the reference's `int += double` cell loops (src/map.cc:157-186) never advance below 1 m
     return mfail(nullptr, LIODOM_E_INVALID, "voxel sizes below 1 m are not supported (the reference's getLocalMap loops do not terminate)");
   const double vox = std::max(voxel_xysize, voxel_zsize) / resolution;
-  if (vox > (1 << kLatBits) - 8) return mfail(nullptr, LIODOM_E_INVALID, "cell size / resolution = %.0f exceeds %d voxels per axis", vox, (1 << kLatBits) - 8);
+  if (vox > (1 << kMaxLatBits) - 8) return mfail(nullptr, LIODOM_E_INVALID, "cell size / resolution = %.0f exceeds %d voxels per axis", vox, (1 << kMaxLatBits) - 8);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
     return mfail(nullptr, LIODOM_E_NODEVICE, "no usable CUDA device (count=%d, requested %d): liodom_b200 has no CPU fallback", ndev, device);
@@ -592,6 +593,8 @@ int liodom_map_create(double voxel_xysize, double voxel_zsize, double resolution
   m.xy = voxel_xysize; m.inv_xy = 1.0 / voxel_xysize; m.xy_half = voxel_xysize / 2.0;   // src/map.cc:70-81
   m.zs = voxel_zsize; m.inv_z = 1.0 / voxel_zsize; m.z_half = voxel_zsize / 2.0;
   m.inv_leaf = 1.0f / (float)resolution;   // pcl::VoxelGrid: inverse_leaf_size_ in float
+  m.lat_bits = 1;
+  while ((1 << m.lat_bits) < (int)std::ceil(vox) + 8) ++m.lat_bits;   // lattice span of a cell + the 2-voxel margins and rounding slack
   m.cap_points = max_points;
   m.cap_new = 1 << 16;
   m.cap_cells = 1 << 16;
