@@ -462,9 +462,12 @@ void LaserOdometer::operator()(std::atomic<bool>& running) {
       const bool ok = process(feats, feat_header, &pose);
       const auto end_t = Clock::now();
       if (ok) {
-        if (!first) stats->addLaserOdometryTime(start_t, end_t);   // the first frame is not timed (src/laser_odometry.cc:108-136)
-        stats->stopFrame(end_t);
+        // both branches of the reference record pose, time and frame span (src/laser_odometry.cc:130-134, :259-263)
         stats->addPose(odom_.matrix());
+        stats->addLaserOdometryTime(start_t, end_t);
+        stats->stopFrame(end_t);
+        // first frame: prev_stamp_ is set BEFORE publishOdom (:127), so its twist divides by zero as the reference's does
+        if (first) prev_stamp_ = feat_header.stamp.toSec();
         if (odom_cb_) odom_cb_(feat_header, odom_);
         publishOdom(feat_header, odom_);
       }
@@ -628,6 +631,28 @@ void liodom_host_make_odometry(const double* pose16, const double* prev_odom16, 
   const Odometry m = LaserOdometer::makeOdometry(h, pose, prev, l2b, prev_stamp, "odom", "base_link");
   out13[0] = m.orientation.x(); out13[1] = m.orientation.y(); out13[2] = m.orientation.z(); out13[3] = m.orientation.w();
   for (int k = 0; k < 3; ++k) { out13[4 + k] = m.position[k]; out13[7 + k] = m.twist_linear[k]; out13[10 + k] = m.twist_angular[k]; }
+}
+
+// Stats::writeResults through the façade (test hook; compared with the reference's own Stats, src/stats.cc:73-132):
+// poses16 [n x 16], nfeats [n] (int64), times_ms [n x 2] = (feature extraction, laser odometry) spans.
+void liodom_host_stats_write(const double* poses16, const long long* nfeats, const double* times_ms, int n, const char* dir) {
+  using namespace liodom;
+  Stats* stats = Stats::getInstance();
+  stats->clear();
+  const Clock::time_point t0 = Clock::now();
+  for (int k = 0; k < n; ++k) {
+    Matrix4d M;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M(i, j) = poses16[(size_t)k * 16 + i * 4 + j];
+    stats->addPose(M);
+    stats->addNumOfFeats((size_t)nfeats[k]);
+    const auto fe = std::chrono::microseconds((long long)(times_ms[2 * k] * 1000.0)), lo = std::chrono::microseconds((long long)(times_ms[2 * k + 1] * 1000.0));
+    stats->addFeatureExtractionTime(t0, t0 + fe);
+    stats->addLaserOdometryTime(t0, t0 + lo);
+    stats->startFrame(t0);
+    stats->stopFrame(t0 + fe + lo);
+  }
+  stats->writeResults(dir);
+  stats->clear();
 }
 
 // The same with sensor_msgs/PointCloud2 messages, as lidarClb receives them: `data` holds the frames'

@@ -6,18 +6,20 @@
  * product (liodom_b200/) never links, imports or calls it.
  *
  * PARITY STATUS
- *   - feature extraction (split, curvature, region selection): restated literally
- *     from the reference's own source; bit-exact by construction.
- *   - registration and map: the arithmetic lives in PCL / FLANN / Eigen / Ceres,
- *     none of which is vendored in /root/reference or installed here.  Inferred
- *     versions (Ubuntu 20.04 / ROS Noetic): PCL 1.10.0, FLANN 1.9.1, Eigen 3.3.7,
- *     Ceres 1.14.0.  Their published algorithms are restated.
- *     The reference ships no tests, golden vectors or fixtures, and cannot be
- *     compiled here (needs ROS/PCL/Ceres/Eigen/cmake): ** parity unpinned **
- *     for kNN tie order, VoxelGrid in-voxel order, the eigen gate within 1e-15 of
- *     equality and the Ceres trust-region loop.  Pins used instead: known-answer
- *     tests from the invariants in SURVEY.md §4 and independent NumPy/SciPy
- *     re-derivations in tests/.
+ *   - PINNED by the reference's own object code: oracle/_ref/libliodom_ref.so is
+ *     /root/reference/src/{feature_extractor,laser_odometry,map,params,shared_data,stats}.cc
+ *     compiled UNMODIFIED (make -C oracle ref) against the test-only API shim oracle/refshim/.
+ *     tests/test_ref_pins_oracle.py: ring split and edge lists bit-exact (A1-A4), LocalMapManager
+ *     (A5), Point2LineFactor residual/Jacobian from the reference's own functor through Jets (A9),
+ *     the whole LaserOdometer::operator() control flow (A6-A11: poses equal to the last bit on
+ *     the synthetic sequences), Map keys / creation order / counts (A12-A13), Stats files.
+ *   - STILL UNPINNED ("parity unpinned" for these only): what the reference delegates to PCL /
+ *     FLANN / Eigen / Ceres / tf.  None is vendored in /root/reference or installed here; inferred
+ *     versions (Ubuntu 20.04 / ROS Noetic): PCL 1.10.0, FLANN 1.9.1, Eigen 3.3.7, Ceres 1.14.0.
+ *     Their published algorithms are restated twice (here and, independently, in refshim/):
+ *     kNN tie order among exactly equal distances, VoxelGrid's in-voxel accumulation order
+ *     (PCL sorts unstably; here: input order), the eigen gate within 1e-15 of equality and the
+ *     Ceres trust-region loop rest on SURVEY.md App. A plus the NumPy/SciPy cross-checks in tests/.
  */
 #ifndef LIODOM_ORACLE_H
 #define LIODOM_ORACLE_H
