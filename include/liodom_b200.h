@@ -113,7 +113,10 @@ int liodom_set_received_map(liodom_ctx* ctx, int lane, const float* xyzi, int n)
 /* Device-side hand-off of the same cloud: liodom_received_map_buffer gives the lane's device buffer
  * (capacity in points), a producer fills it (liodom_map_get_local_device), liodom_commit_received_map
  * sets its size and rebuilds the voxel hash.  Replaces the ROS hop map_local -> mapClb ->
- * SharedData::setLocalMap (src/liodom_node.cc:57-64) when both processes' work lives on one GPU. */
+ * SharedData::setLocalMap (src/liodom_node.cc:57-64) when both processes' work lives on one GPU.
+ * liodom_received_map_buffer waits for the context's scans in flight (they read the buffer); the producer must have
+ * finished writing (liodom_map_get_local_device synchronises) before liodom_commit_received_map is called, and no
+ * liodom_scan_batch may be enqueued between the two calls. */
 int liodom_received_map_buffer(liodom_ctx* ctx, int lane, void** dev_xyzi, int* cap);
 int liodom_commit_received_map(liodom_ctx* ctx, int lane, int n);
 

@@ -197,13 +197,29 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   p.chunks = p.Ncap / kChunk;
   p.Ecap = P.scan_lines * P.scan_regions * (P.edges_per_region + 1);
   p.slots = P.prev_frames + 1;
-  p.Rcap = P.mapping ? (P.max_received_map > 0 ? P.max_received_map : 1 << 20) : 0;
-  p.Mcap = p.slots * p.Ecap + p.Rcap;
   p.Wcap = p.slots * p.Ecap;
+  // The per-cell point count shares a 32-bit word with the generation tag (kCntBits = 20 bits): keep the whole kNN
+  // target below 2^20 points, then no cell can overflow its count even if every point fell into one voxel.
+  const long long cnt_limit = (1ll << kCntBits) - 1;
+  if ((long long)p.Wcap >= cnt_limit) {
+    fail(nullptr, LIODOM_E_INVALID, "window of %d points (prev_frames+1 slabs x %d edges) exceeds the voxel-hash limit of %lld points", p.Wcap, p.Ecap, cnt_limit);
+    liodom_ctx_destroy(c); return LIODOM_E_INVALID;
+  }
+  p.Rcap = P.mapping ? (P.max_received_map > 0 ? P.max_received_map : (int)std::min<long long>(1 << 20, cnt_limit - p.Wcap)) : 0;
+  if ((long long)p.Wcap + p.Rcap > cnt_limit) {
+    fail(nullptr, LIODOM_E_INVALID, "max_received_map %d + window %d exceed the voxel-hash limit of %lld points", p.Rcap, p.Wcap, cnt_limit);
+    liodom_ctx_destroy(c); return LIODOM_E_INVALID;
+  }
+  p.Mcap = p.Wcap + p.Rcap;
   p.vg_blocks = (P.filter_local_map && !P.mapping) ? (p.Wcap + kVgTile - 1) / kVgTile : 0;
   int h = 1024; while (h < p.Mcap + p.Mcap / 8) h <<= 1;   // load factor <= 0.89 even if every point had its own voxel; typically < 0.2
   p.Hcap = h;
   p.Bwords = h / 2;   // 16 filter bits per hash slot: a few % false positives (each costs one extra probe, never a wrong answer)
+  if (extract_smem_needed(p) > (size_t)kMaxDynSmem) {
+    fail(nullptr, LIODOM_E_INVALID, "scan_lines x scan_regions x edges_per_region needs %zu bytes of shared memory per CTA (limit %d)", extract_smem_needed(p), kMaxDynSmem);
+    liodom_ctx_destroy(c); return LIODOM_E_INVALID;
+  }
+  CKC(configure_extract_kernels());   // per device: a second context on another GPU needs its own opt-in
   const size_t B = batch, L = P.scan_lines;
   CKC(dalloc(c, &d.scan, B));
   CKC(dalloc(c, &d.ring_id, B * p.Ncap, false));
@@ -552,6 +568,8 @@ int liodom_set_received_map(liodom_ctx* c, int lane, const float* xyzi, int n) {
 int liodom_received_map_buffer(liodom_ctx* c, int lane, void** dev_xyzi, int* cap) {
   int rc = check_lane(c, lane); if (rc) return rc;
   if (!c->params.mapping) return fail(c, LIODOM_E_INVALID, "context was created with mapping=0");
+  // The producer writes on ITS stream: scans still in flight here (their hash build reads this buffer) must finish first.
+  rc = liodom_sync(c); if (rc) return rc;
   if (dev_xyzi) *dev_xyzi = c->d.received + (size_t)lane * c->d.p.Rcap;
   if (cap) *cap = c->d.p.Rcap;
   return 0;

@@ -26,6 +26,7 @@ constexpr int kMaxSlots = 64;       // window slabs upper bound (prev_frames + 1
 constexpr int kRingSmemCap = 6144;  // ring points kept in shared memory by k_extract
 constexpr unsigned kGenBits = 12;   // hash generation tag width
 constexpr unsigned kCntBits = 20;
+constexpr int kMaxDynSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kVgTile = 2048;       // keys per CTA of the window-filter radix sort (256 threads x 8)
 
 // One slot of the open-addressing voxel hash: packed cell key (generation | iz | iy | ix), first
@@ -186,6 +187,8 @@ int launch_window_update(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_lmap_add(const DevBuffers& d, cudaStream_t s, int lane, const float4* pts_dev, int n);
 int launch_lmap_gather(const DevBuffers& d, cudaStream_t s, int lane, float4* out);
 int extract_ring_cap(const DevParams& p);
+cudaError_t configure_extract_kernels();          // per device, from liodom_ctx_create
+size_t extract_smem_needed(const DevParams& p);   // largest dynamic shared memory request of k_extract / k_compact
 int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings);
 int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr);
 int launch_associate_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, int rank, int world);

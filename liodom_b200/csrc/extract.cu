@@ -611,10 +611,22 @@ int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   return 3;
 }
 
+// Dynamic shared memory above 48 KB is an opt-in PER DEVICE: liodom_ctx_create calls this after cudaSetDevice, so
+// every device a context lives on gets the limit raised (to the architectural maximum: contexts with different
+// parameters may share a device).  Returns the first CUDA error.
+cudaError_t configure_extract_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
+size_t extract_smem_needed(const DevParams& p) {
+  const size_t a = extract_smem_bytes(p, extract_ring_cap(p)), b = (size_t)(p.scan_lines * p.scan_regions + 32) * sizeof(int);
+  return a > b ? a : b;
+}
+
 int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings) {
   const int ring_cap = extract_ring_cap(d.p);
   const size_t sm = extract_smem_bytes(d.p, ring_cap);
-  cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   k_extract<<<dim3(nrings, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, 0, ring0);
   return 1;
 }
@@ -627,11 +639,6 @@ int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
 int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys) {
   const int ring_cap = extract_ring_cap(d.p);
   const size_t sm = extract_smem_bytes(d.p, ring_cap);
-  static size_t configured = 0;
-  if (sm > configured) {
-    cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    configured = sm;
-  }
   k_extract<<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0, 0);
   const int LR = d.p.scan_lines * d.p.scan_regions;
   k_compact<<<lr.nlanes, 1024, (LR + 32) * sizeof(int), s>>>(d, lr.lane0);

@@ -6,6 +6,7 @@
 // explicit *_rn intrinsics and the file is compiled with -fmad=false.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace liodom {
@@ -53,6 +54,12 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
   load_win_view(d, lane_b, &v);
   const WinState& ws = d.wstate[lane_b];
   const int npts = ws.hash_points;
+  // The 12-bit tag only distinguishes generations because the host clears the tables and resets ws.gen before it
+  // wraps (hash_generation_guard in cabi.cu).  A caller that forgot the guard must fail loudly, not reuse stale cells.
+  if (ws.gen >> kGenBits) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("liodom_b200: voxel-hash generation %u overflowed its %u-bit tag (missing hash_generation_guard)\n", ws.gen, kGenBits);
+    __trap();
+  }
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned mask = (unsigned)d.p.Hcap - 1u;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
@@ -337,11 +344,7 @@ __global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
 
 int launch_predict(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   k_predict<<<lr.nlanes, 32, 0, s>>>(d, lr.lane0);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_edge_order, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrderChunk * 8);
-    configured = true;
-  }
+  static_assert(kOrderChunk * 8 <= 48 * 1024, "k_edge_order stays below the 48 KB default: no per-device opt-in needed");
   k_edge_order<<<dim3((d.p.Ecap + kOrderChunk - 1) / kOrderChunk, lr.nlanes), 1024, kOrderChunk * 8, s>>>(d, lr.lane0);
   return 2;
 }

@@ -341,7 +341,7 @@ LaserOdometer::~LaserOdometer() {}
 
 bool LaserOdometer::ensureContext() {
   if (ctx_) return true;
-  ctx_ = make_ctx(params, 2048, (int)params->local_map_size_, params->mapping_ ? (1 << 20) : 0);
+  ctx_ = make_ctx(params, 2048, (int)params->local_map_size_, 0);   // 0: the library default capacity for the received map
   if (ctx_) liodom_odom_set_laser_to_base(ctx_.get(), 0, laser_to_base_.matrix().m);
   return (bool)ctx_;
 }

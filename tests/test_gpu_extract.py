@@ -209,3 +209,35 @@ def test_split_points_near_bin_and_range_boundaries(cuda_lib, lines):
     assert len(diff) <= g["n_ambiguous"], (len(diff), g["n_ambiguous"])
     assert (g["ring_of_point"] >= 0).sum() > len(s) // 2
     ctx.close()
+
+
+def test_large_region_configs_and_limits(cuda_lib):
+    """k_compact / k_extract raise their dynamic shared-memory limit per device at context creation: a 64 x 256
+    region grid (66 KB of prefix-sum scratch, above the 48 KB default) must run; a configuration whose
+    selection scratch cannot fit the 227 KB of an SM is refused at creation, not at launch."""
+    s = get_sequence("hdl64", 1000, 1)[0][0]
+    kw = dict(scan_regions=200, edges_per_region=1)
+    op = oracle.make_params(**kw)
+    ctx = api.Context(max_points=131072, **kw)
+    _cmp_extract(ctx, op, s)
+    ctx.close()
+    with pytest.raises(api.LiodomError):
+        api.Context(max_points=131072, scan_regions=256, edges_per_region=255)
+    with pytest.raises(api.LiodomError):      # window + received map beyond the voxel hash's 2^20-point limit
+        api.Context(max_points=131072, mapping=1, max_received_map=1 << 20)
+
+
+def test_two_contexts_on_two_devices(cuda_lib):
+    """One process, one context per GPU: each device needs its own shared-memory opt-in."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = get_sequence("hdl64", 1000, 1)[0][0]
+    op = oracle.make_params()
+    sp = oracle.split(op, s)
+    oe = oracle.extract(op, sp["rings"], sp["offsets"])["edges"]
+    for dev in (1, 0):
+        ctx = api.Context(max_points=131072, device=dev)
+        g = ctx.extract(s)
+        assert np.array_equal(g.view(np.uint32), oe.view(np.uint32)), dev
+        ctx.close()
