@@ -42,9 +42,15 @@ def parse():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("LIODOM_BENCH_LANES", "128")),
                     help="independent sequences per GPU processed by one step")
     ap.add_argument("--sensor", default="hdl64")
-    ap.add_argument("--config", default="c1", choices=["c1", "c2", "c3"],
+    ap.add_argument("--config", default="c1", choices=["c1", "c2", "c3", "c4"],
                     help="c1: the headline workload (launch/liodom.launch); c2 / c3: the other BASELINE.json shapes "
-                         "(OS1-128 organised clouds; scan_regions/edges_per_region doubled, prev_frames=20), for profiles/ only")
+                         "(OS1-128 organised clouds; scan_regions/edges_per_region doubled, prev_frames=20), for profiles/ only; "
+                         "c4: liodom_mapping_node's map build over a 4000-frame loop (Map::updateMap / getLocalMap / getMap)")
+    ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
+                    help="sequences: independent sequences per GPU (the headline); sharded: ONE 1M-point scan stream, ring-sharded "
+                         "extraction + edge-sharded registration across the GPUs with a 29-double NCCL all-reduce per LM evaluation")
+    ap.add_argument("--frames", type=int, default=4000, help="frames of the c4 loop")
+    ap.add_argument("--no-sharded-block", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-pass", action="store_true")
     ap.add_argument("--no-single-stream", action="store_true")
@@ -382,6 +388,14 @@ def run_b200(args):
     ctx.close()
     clocks = sampler.stop()
 
+    # ---------------- point-sharded 1M-point stream (BASELINE config 5, second half; short, outside the headline) -----
+    sharded = None
+    if not args.no_sharded_block and args.config == "c1":
+        del dev_scans, host_steps
+        torch.cuda.empty_cache()
+        sharded = point_sharded_run(api, torch, dist, rank, world, local, nframes=7, warm=3)
+        sharded["note"] = "7 frames (3 warm-up): the 15-frame window is still filling; `bench.py --mode sharded` runs the full-window version"
+
     # ---------------- single stream (the reference's own shape: one sequence through liodom_node) -------------
     single = None
     if rank == 0 and not args.no_single_stream:
@@ -453,6 +467,8 @@ def run_b200(args):
         out["stages"] = stages
     if single is not None:
         out["single_stream"] = single
+    if sharded is not None:
+        out["point_sharded"] = sharded
     if cpu is not None:
         out["cpu_baseline"] = cpu
     emit(out)
@@ -497,6 +513,200 @@ def single_stream_block(api, torch, dev, local, scans, npts, kw, P, W, K, width,
     return {"lanes": 1, "value": round(out["device"][0], 1), "ms_per_scan": round(out["device"][1], 4),
             "e2e_value": round(out["e2e"][0], 1), "e2e_ms_per_scan": round(out["e2e"][1], 4), "unit": UNIT, "frames_timed": K1,
             "note": "one sequence, full window; the GPU is mostly idle at this shape (latency of ~20 dependent kernels)"}
+
+
+def point_sharded_run(api, torch, dist, rank, world, local, nframes, warm, sensor="hdl64_1m", scan_regions=64):
+    """BASELINE.json config 5, second half: ONE stream of 1M-point scans (64 rings x 15,625 az; scan_regions=64 so that
+    E ~ 45k edges, SURVEY.md §8(d) note F5).  world == 1: the ordinary single-GPU path on that shape.  world > 1: every
+    rank receives the same scan; extraction shards by ring, association / LM evaluation by edge, one all-gather of the
+    edge slots per scan and one 29-double ncclAllReduce per LM evaluation; rank 0 also runs the single-GPU path on the
+    same scans (untimed against the others) as the parity reference and the same-shape baseline."""
+    from liodom_b200 import synth
+    dev = torch.device("cuda", local)
+    scans, _ = synth.sequence(sensor, 1000, nframes)
+    kw = dict(prev_frames=15, scan_regions=scan_regions, max_points=1 << 20, device=local)
+    dscans = [torch.from_numpy(s).to(dev) for s in scans]
+
+    def run(ctx, timed_from):
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        poses, ne = [], []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for f in range(nframes):
+            if f == timed_from:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                ev0.record(stream)
+            ctx.scan_batch_ptrs([dscans[f].data_ptr()], [len(scans[f])], 16, on_device=True)
+            if f < timed_from:
+                ctx.sync()
+            if f >= timed_from - 1:
+                p, n = ctx.results()      # poses are read back every frame (the stream is sequential anyway)
+                poses.append(p[0].copy())
+                ne.append(int(n[0]))
+        ev1.record(stream)
+        ctx.sync()
+        return ev0.elapsed_time(ev1) / (nframes - timed_from), poses, ne
+
+    out = {"sensor": sensor, "points_per_scan": int(np.mean([len(s) for s in scans])), "scan_regions": scan_regions,
+           "frames_timed": nframes - warm, "world": world}
+    single_ms = None
+    single_poses = None
+    if rank == 0:
+        # the ordinary single-GPU path on the same scans: the job's time at world == 1; at world > 1 the parity reference
+        # and same-shape baseline (only rank 0 runs it, before the sharded leg; `run` must not hit the barrier then)
+        ctx = api.Context(batch=1, **kw)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        single_poses, ne = [], []
+        for f in range(nframes):
+            if f == warm:
+                torch.cuda.synchronize()
+                e0.record(stream)
+            ctx.scan_batch_ptrs([dscans[f].data_ptr()], [len(scans[f])], 16, on_device=True)
+            p, n = ctx.results()
+            if f >= warm - 1:
+                single_poses.append(p[0].copy())
+                ne.append(int(n[0]))
+        e1.record(stream)
+        ctx.sync()
+        single_ms = e0.elapsed_time(e1) / (nframes - warm)
+        d = ctx.scan_diag(0)
+        out.update({"edges_per_scan": int(np.mean(ne)), "map_points": int(d.n_map[0]), "single_gpu_ms_per_scan": round(single_ms, 4)})
+        ctx.close()
+    if world > 1:
+        uid = [api.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx = api.Context(batch=1, **kw)
+        ctx.shard_init(rank, world, uid[0])
+        l0 = ctx.launch_count
+        ms, poses, ne = run(ctx, warm)
+        launches = ctx.launch_count - l0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank must hold bitwise the same poses (the LM controller is replicated)
+        mine = torch.from_numpy(np.stack(poses)).to(dev)
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        same = torch.tensor([1.0 if torch.equal(mine, ref0) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ctx.close()
+        if rank == 0:
+            worst = max(max(pose_err(a, b)) for a, b in zip(poses, single_poses))
+            out.update({"sharded_ms_per_scan": round(float(t.item()), 4), "value": round(1e3 / float(t.item()), 2), "unit": "scans/s",
+                        "speedup_vs_single_gpu": round(single_ms / float(t.item()), 3),
+                        "ranks_bitwise_equal": bool(same.item() == 1.0), "worst_pose_diff_vs_single_gpu": worst,
+                        "kernel_launches_per_scan": round(launches / nframes, 1),
+                        "collectives": "1 grouped all-gather of the edge slots + up to 10 ncclAllReduce(29 x f64) per scan, on the context's stream"})
+    elif rank == 0:
+        out.update({"value": round(1e3 / single_ms, 2), "unit": "scans/s"})
+    return out
+
+
+def run_sharded(args):
+    """bench.py --mode sharded [--gpus N]: the point-sharded 1M-point stream as its own JSON line (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from liodom_b200 import api
+    rank, world, local = dist_env()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    K, W = args.steps, max(args.warmup, 1)
+    r = point_sharded_run(api, torch, dist, rank, world, local, 16 + W + K, 16 + W)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms = r.get("sharded_ms_per_scan", r.get("single_gpu_ms_per_scan"))
+    emit({"metric": "scans_per_sec_1m_point_stream_point_sharded", "value": r["value"], "unit": "scans/s", "n_gpus": world, "steps": K, "warmup": W,
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 selection/kNN, f64 gates+LM",
+          "data": "synthetic",
+          "config": {"workload": "C5b: one stream of 1M-point scans (64 x 15,625), scan_regions=64, prev_frames=15, full window; "
+                                 "ring-sharded extraction, edge-sharded association + LM, replicated window", "pre_roll_steps": 16},
+          "point_sharded": r})
+
+
+def run_c4(args):
+    """BASELINE.json config 4: liodom_mapping_node's per-message sequence (src/liodom_mapping_node.cc:45-90) over a
+    closed loop: Map::updateMap + Map::getLocalMap every frame, Map::getMap every 100th, both shipped parameter sets,
+    GPU (C ABI, host buffers in / out) against the oracle Map on the host, maps compared bit for bit."""
+    import oracle
+    from liodom_b200 import api, synth
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    nfr = args.frames
+    t0 = time.time()
+    ctx = api.Context(max_points=131072, device=local)
+    clouds, poses = [], []
+    T0 = synth.gt_pose(1000, 0, traj=1)
+    for f in range(nfr):      # edge clouds from the GPU extractor (untimed), ground-truth poses of the ~4 km circuit
+        clouds.append(ctx.extract(synth.scan("hdl64", 1000, f, traj=1)))
+        poses.append(np.linalg.inv(T0) @ synth.gt_pose(1000, f, traj=1))
+    ctx.close()
+    gen_s = time.time() - t0
+    res = {}
+    for name, (xy, z, cxy, cz) in {"liodom_mapping.launch": (20.0, 25.0, 2, 1), "liodom.launch": (30.0, 35.0, 3, 2)}.items():
+        gm = api.Map(xy, z, 0.4, device=local, max_points=1 << 23)
+        gm.update(clouds[0], poses[0])          # warm-up (allocations, first kernels)
+        gm.get_local_map(poses[0], cxy, cz)
+        gm.close()
+        gm = api.Map(xy, z, 0.4, device=local, max_points=1 << 23)
+        nloc = nfull = 0
+        t_upd = t_loc = t_full = 0.0
+        g_samples = {}
+        for f, (c, T) in enumerate(zip(clouds, poses)):
+            a = time.perf_counter()
+            gm.update(c, T)
+            b = time.perf_counter()
+            loc = gm.get_local_map(T, cxy, cz)
+            d = time.perf_counter()
+            t_upd += b - a
+            t_loc += d - b
+            nloc += len(loc)
+            if f % 100 == 0:      # the mapping node publishes the full map only when someone listens; BASELINE: every 100th frame
+                a = time.perf_counter()
+                full = gm.get_map()
+                t_full += time.perf_counter() - a
+                nfull += 1
+                g_samples[f] = (loc.copy(), len(full))
+        tg = t_upd + t_loc + t_full
+        npts, ncells = gm.size()
+        gfull = gm.get_map()
+        gk, gc = gm.cells()
+        om = oracle.Map(xy, z, 0.4)
+        ok_local = True
+        t0c = time.perf_counter()
+        for f, (c, T) in enumerate(zip(clouds, poses)):
+            om.update(c, T)
+            ol = om.get_local_map(T, cxy, cz)
+            if f % 100 == 0:
+                of = om.get_map()
+                ok_local = ok_local and np.array_equal(ol.view(np.uint32), g_samples[f][0].view(np.uint32)) and len(of) == g_samples[f][1]
+        tc = time.perf_counter() - t0c
+        okk, okc = om.cells()
+        same = bool(np.array_equal(gfull.view(np.uint32), om.get_map().view(np.uint32)) and np.array_equal(gk, okk) and np.array_equal(gc, okc))
+        assert same and ok_local, "C4 %s: GPU map differs from the oracle map" % name
+        res[name] = {"voxel_xysize": xy, "voxel_zsize": z, "cells_xy": cxy, "cells_z": cz, "frames": nfr,
+                     "edges_per_frame": int(np.mean([len(c) for c in clouds])), "map_points": npts, "cells": ncells,
+                     "local_map_points_per_frame": int(nloc / nfr), "getMap_calls": nfull,
+                     "gpu_ms_per_frame": round(tg / nfr * 1e3, 4),
+                     "gpu_ms": {"updateMap": round(t_upd / nfr * 1e3, 4), "getLocalMap": round(t_loc / nfr * 1e3, 4), "getMap_per_call": round(t_full / max(nfull, 1) * 1e3, 3)},
+                     "cpu_oracle_ms_per_frame": round(tc / nfr * 1e3, 4),
+                     "map_and_sampled_local_maps_bitwise_equal_to_oracle": True}
+        gm.close()
+    head = res["liodom_mapping.launch"]
+    emit({"metric": "c4_map_build_ms_per_frame", "value": head["gpu_ms_per_frame"], "unit": "ms/frame", "n_gpus": 1, "steps": nfr, "warmup": 1,
+          "ms_per_step": head["gpu_ms_per_frame"], "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32 centroids, f64 keys",
+          "data": "synthetic",
+          "config": {"workload": "C4: %d-frame closed loop (~4 km rounded square) of HDL-64 edge clouds + ground-truth poses through updateMap -> "
+                                 "getLocalMap (every frame) -> getMap (every 100th), launch/liodom_mapping.launch:15-19 and launch/liodom.launch:46-50 params" % nfr},
+          "e2e": {"value": head["gpu_ms_per_frame"], "unit": "ms/frame", "note": "the Map C ABI takes and returns HOST buffers: every number here is end to end"},
+          "cpu_baseline": {"value": head["cpu_oracle_ms_per_frame"], "unit": "ms/frame", "cores": 1, "kind": "port",
+                           "sample": "the same %d frames through the oracle Map (restated src/map.cc + PCL VoxelGrid), one thread as the reference" % nfr},
+          "results": res, "synth_seconds": round(gen_s, 1)})
 
 
 def cpu_baseline_single_stream(seqs, okw=None, width=0, height=0, name="C1"):
@@ -599,6 +809,10 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_c4(args)
+    elif args.mode == "sharded":
+        run_sharded(args)
     else:
         run_b200(args)
 

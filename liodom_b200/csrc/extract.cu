@@ -492,13 +492,16 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
   }
   __syncthreads();
   // The only coupling between the regions of a ring is picked_: a pick within 5 points of the end of
-  // region r suppresses (gap-limited) up to 5 leading points of region r+1.  Each region's spill is a
-  // 5-bit mask; a region has to be re-run only if one of its speculative picks is in the mask of its
-  // (final) predecessor.  Warp 0 walks the regions in order; without clashes this is O(R) checks.
+  // region r suppresses (gap-limited) up to 5 points beyond it.  Each region's spill is a 5-bit mask
+  // over the indices that follow it; `carry` accumulates the spills of the regions behind, shifted to the
+  // current region's start (regions shorter than 5 points — edges_per_region < 5 — pass part of a spill on
+  // to their successors).  A region is re-run only if one of its speculative picks is suppressed by the
+  // (final) carry.  Warp 0 walks the regions in order; without clashes this is O(R) checks.
   if (w == 0) {
-    unsigned spill_prev = 0;   // mask of region r-1 over the indices lo_r + b
+    unsigned carry = 0;        // bit b: ring index lo_r + b is suppressed by a pick of an earlier region
     for (int r = 0; r < R; ++r) {
       const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
+      const unsigned spill_prev = carry & 0x1fu;
       int np = npicks[r];
       bool rerun = false;
       if (spill_prev) {
@@ -523,8 +526,9 @@ __global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ri
         }
         if (ln == 0) npicks[r] = np;
         __syncwarp();
-        spill_prev = region_spill(rv, picks + r * E1, np, hi, ln);
-      } else spill_prev = s_spill[r];
+      }
+      const unsigned spill_out = rerun ? region_spill(rv, picks + r * E1, np, hi, ln) : s_spill[r];
+      carry = ((hi - lo) >= 32 ? 0u : (carry >> (hi - lo))) | spill_out;
     }
   }
   __syncthreads();
@@ -614,14 +618,27 @@ int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
 // Dynamic shared memory above 48 KB is an opt-in PER DEVICE: liodom_ctx_create calls this after cudaSetDevice, so
 // every device a context lives on gets the limit raised (to the architectural maximum: contexts with different
 // parameters may share a device).  Returns the first CUDA error.
-cudaError_t configure_extract_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(k_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+template <typename K>
+static cudaError_t raise_dynamic_smem_limit(K kernel) {
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  // the opt-in limit covers static + dynamic shared memory of a CTA
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
-size_t extract_smem_needed(const DevParams& p) {
+cudaError_t configure_extract_kernels() {
+  cudaError_t e = raise_dynamic_smem_limit(k_extract);
+  if (e != cudaSuccess) return e;
+  return raise_dynamic_smem_limit(k_compact);
+}
+size_t extract_smem_needed(const DevParams& p) {   // + 4 KB for the kernels' static shared memory
   const size_t a = extract_smem_bytes(p, extract_ring_cap(p)), b = (size_t)(p.scan_lines * p.scan_regions + 32) * sizeof(int);
-  return a > b ? a : b;
+  return (a > b ? a : b) + 4096;
 }
 
 int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings) {

@@ -511,6 +511,49 @@ __device__ __forceinline__ void knn_scan_row(const HashEntry* __restrict__ tab, 
   }
 }
 
+// Fallback of the 5-NN search: edges whose 5th neighbour is not proven inside the kCell radius.  The whole warp
+// walks the 25 x-rows of the owner's 5^3 cube (one row per lane; rows and cells beyond the owner's current 5th
+// best or the 1 m gate are skipped on their bounds, the 27 cells of level 1 are masked out), then the per-lane
+// lists are merged by 5 rounds of warp arg-min.  Must be called by all 32 lanes; `want`: this lane owns a query.
+__device__ __forceinline__ void knn_fallback_warp(const HashEntry* __restrict__ tab, const float4* __restrict__ sorted,
+                                                  const unsigned* __restrict__ bloom, unsigned hmask, unsigned bmask, unsigned gen,
+                                                  bool want, float qx, float qy, float qz, int cx, int cy, int cz, Knn5& k, int ln) {
+  unsigned need = __ballot_sync(0xffffffffu, want && (unsigned)(k.k[4] >> 32) >= __float_as_uint(kProvenD2));
+  while (need) {
+    const int owner = __ffs(need) - 1;
+    need &= need - 1;
+    const float jx = __shfl_sync(0xffffffffu, qx, owner), jy = __shfl_sync(0xffffffffu, qy, owner), jz = __shfl_sync(0xffffffffu, qz, owner);
+    const int jcx = __shfl_sync(0xffffffffu, cx, owner), jcy = __shfl_sync(0xffffffffu, cy, owner), jcz = __shfl_sync(0xffffffffu, cz, owner);
+    const unsigned ubb = __shfl_sync(0xffffffffu, (unsigned)(k.k[4] >> 32), owner);
+    const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
+    Knn5 l;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {   // lane 0 inherits the owner's list, the others start empty
+      const unsigned long long v = __shfl_sync(0xffffffffu, k.k[r], owner);
+      l.k[r] = ln == 0 ? v : kEmptyCand;
+    }
+    for (int rr = ln; rr < kFbSide * kFbSide; rr += 32) {
+      const int dy = rr % kFbSide - kFbRadius, dz = rr / kFbSide - kFbRadius;
+      const unsigned inner = (abs(dy) <= 1 && abs(dz) <= 1) ? (7u << (kFbRadius - 1)) : 0u;
+      knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, jcx - kFbRadius, kFbSide, inner, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {   // warp arg-min on the 64-bit heads: high word, then low word among ties
+      const unsigned hh = (unsigned)(l.k[0] >> 32), hl = (unsigned)l.k[0];
+      const unsigned mh = __reduce_min_sync(0xffffffffu, hh);
+      const unsigned ml = __reduce_min_sync(0xffffffffu, hh == mh ? hl : 0xffffffffu);
+      const int wl = __ffs(__ballot_sync(0xffffffffu, hh == mh && hl == ml)) - 1;
+      if (ln == owner) k.k[r] = ((unsigned long long)mh << 32) | ml;
+      if (ln == wl) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) l.k[q] = l.k[q + 1];
+        l.k[4] = kEmptyCand;
+      }
+    }
+  }
+}
+
 // Line gate and residual block of one edge (src/laser_odometry.cc:324-361): centroid and scatter of the five
 // neighbours in double, eigenvalues, lambda2 > 3 lambda1, block {c, a, b, valid}.  nn_idx[0] < 0: fewer than five
 // neighbours within 1 m.  Returns true when the edge yields a residual block.
@@ -663,44 +706,7 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
 #pragma unroll
       for (int r = 0; r < 5; ++r) k.k[r] = res[r];   // the merged list, uniform over the group
     }
-    // ---- fallback: edges whose 5th neighbour is not proven inside the kCell radius.  The whole warp
-    // walks the 25 x-rows of the owner's 5^3 cube (one row per lane; rows and cells
-    // beyond the owner's current 5th best or the 1 m gate are skipped on their bounds, the 27 cells of
-    // level 1 are masked out), then the per-lane lists are merged by 5 rounds of warp arg-min.
-    unsigned need = __ballot_sync(0xffffffffu, searchable && gl == 0 && (unsigned)(k.k[4] >> 32) >= __float_as_uint(kProvenD2));
-    while (need) {
-      const int owner = __ffs(need) - 1;
-      need &= need - 1;
-      const float jx = __shfl_sync(0xffffffffu, qx, owner), jy = __shfl_sync(0xffffffffu, qy, owner), jz = __shfl_sync(0xffffffffu, qz, owner);
-      const int jcx = __shfl_sync(0xffffffffu, cx, owner), jcy = __shfl_sync(0xffffffffu, cy, owner), jcz = __shfl_sync(0xffffffffu, cz, owner);
-      const unsigned ubb = __shfl_sync(0xffffffffu, (unsigned)(k.k[4] >> 32), owner);
-      const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
-      Knn5 l;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {   // lane 0 inherits the owner's list, the others start empty
-        const unsigned long long v = __shfl_sync(0xffffffffu, k.k[r], owner);
-        l.k[r] = ln == 0 ? v : kEmptyCand;
-      }
-      for (int rr = ln; rr < kFbSide * kFbSide; rr += 32) {
-        const int dy = rr % kFbSide - kFbRadius, dz = rr / kFbSide - kFbRadius;
-        const unsigned inner = (abs(dy) <= 1 && abs(dz) <= 1) ? (7u << (kFbRadius - 1)) : 0u;
-        knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, jcx - kFbRadius, kFbSide, inner, jcy + dy, jcz + dz, jx, jy, jz, ub, l);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {   // warp arg-min on the 64-bit heads: high word, then low word among ties
-        const unsigned hh = (unsigned)(l.k[0] >> 32), hl = (unsigned)l.k[0];
-        const unsigned mh = __reduce_min_sync(0xffffffffu, hh);
-        const unsigned ml = __reduce_min_sync(0xffffffffu, hh == mh ? hl : 0xffffffffu);
-        const int wl = __ffs(__ballot_sync(0xffffffffu, hh == mh && hl == ml)) - 1;
-        if (ln == owner) k.k[r] = ((unsigned long long)mh << 32) | ml;
-        if (ln == wl) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) l.k[q] = l.k[q + 1];
-          l.k[4] = kEmptyCand;
-        }
-      }
-    }
+    knn_fallback_warp(tab, sorted, bloom, hmask, bmask, gen, searchable && gl == 0, qx, qy, qz, cx, cy, cz, k, ln);
     // G == 1 (large batches): the search ends here and the five neighbours go to k_line_gate, so that the search
     // kernel's register budget is not shared with the FP64 eigen-solver (no spills to speak of: -13 % at 128 lanes).
     // G > 1 (few edges in flight): gate in place — one launch less matters more there.
@@ -731,6 +737,204 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
     }
   }
   if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
+}
+
+// ---------------------------------------------------------------------------------------
+// Large batches: CTA-level association with work-balanced warps (the G == 1 kernel's successor).
+//
+// ncu on the thread-per-edge kernel (profiles/step_r02b_lanes128.txt): its candidate loop runs with 7.5 of 32 lanes
+// active.  The cause is not the per-cell lock-step but the work itself: per edge the own cell holds 29 points on
+// average and the neighbour cells that survive the own cell's bound another 40, with a heavy tail (p99 270,
+// max 680), and 32 Morton-consecutive edges reach mean/max = 0.38.  Sorting the edges by their exact remaining work
+// gives 0.98.  So a CTA takes 128 Morton-consecutive edges (locality: their buckets are neighbours) and runs
+//   phase 0  one thread per edge: transform, occupancy bits of the cube, probe of the own cell;
+//   sort     counting sort of the CTA's edges by own-bucket length (shared memory) -> thread <-> edge assignment;
+//   phase 1  own bucket scanned (bound), then the neighbour cells the bound cannot exclude are probed and LISTED
+//            (start, count) in shared memory;
+//   sort     by listed work;
+//   phase 2  every lane walks its list in one flattened loop (4 points per iteration, refill = one shared load);
+//   fallback / output as in the thread-per-edge kernel.
+// The selection itself (knn_offer, the (d2, index) order, the pruning rules) is unchanged, so results are
+// bit-identical; only which thread handles which edge changes.
+// ---------------------------------------------------------------------------------------
+constexpr int kCtaQ = 128;      // edges per CTA (8 CTAs per SM: the barriers of one CTA hide behind the others)
+constexpr int kSegCap = 12;     // listed neighbour buckets per edge (the rest, if any, is scanned inline)
+
+struct AssocSmem {
+  float qx[kCtaQ], qy[kCtaQ], qz[kCtaQ];
+  unsigned occ[kCtaQ];                    // bits 0-26: occupancy of the cube, bit 31: searchable
+  unsigned own_start[kCtaQ], own_cnt[kCtaQ];
+  float ub[kCtaQ];                        // known upper bound of the 5th-best d2 (3e38: none)
+  int edge[kCtaQ];                        // edge index, -1: no edge in this slot
+  unsigned long long k[5][kCtaQ];
+  uint2 seg[kSegCap][kCtaQ];
+  unsigned char nseg[kCtaQ];
+  unsigned short perm[kCtaQ];
+  int hist[64];
+};
+
+// Counting sort of the CTA's kCtaQ items by a 6-bit key: perm[pos] = item.  All threads call it (barriers inside).
+// Shared-memory atomics are aggregated per warp (lanes with equal keys elect a leader): most keys of a warp coincide.
+__device__ __forceinline__ void cta_sort_by_key(AssocSmem& sm, int item, int key) {
+  const int tid = threadIdx.x, ln = tid & 31;
+  if (tid < 64) sm.hist[tid] = 0;
+  __syncthreads();
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << ln) - 1u));
+  if (ln == leader) atomicAdd(&sm.hist[key], __popc(peers));
+  __syncthreads();
+  if (tid < 32) {   // exclusive prefix over 64 bins, two per lane
+    const int a = sm.hist[2 * tid], b = sm.hist[2 * tid + 1];
+    int incl = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+    sm.hist[2 * tid] = incl - a - b; sm.hist[2 * tid + 1] = incl - b;
+  }
+  __syncthreads();
+  int base = 0;
+  if (ln == leader) base = atomicAdd(&sm.hist[key], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  sm.perm[base + rank] = (unsigned short)item;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCtaQ, 8) k_associate_cta(DevBuffers d, int lane0, int outer_it, int force,
+                                                             const double* pose_override, int shard_rank, int shard_world) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y;
+  const OdomState& os = d.ostate[lane_b];
+  const bool active = force || os.init;
+  const int share = shard_world > 1 ? (((os.n_edges + shard_world - 1) / shard_world + 31) & ~31) : 0;
+  const int E = shard_world > 1 ? min(os.n_edges, (shard_rank + 1) * share) : os.n_edges;
+  const int t0 = shard_rank * share + blockIdx.x * kCtaQ;
+  if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
+  if (!active || t0 >= E) return;   // uniform over the CTA
+  __shared__ AssocSmem sm;
+  const int tid = threadIdx.x, ln = tid & 31;
+  const WinState& ws = d.wstate[lane_b];
+  const double* T = pose_override ? pose_override : os.odom;
+  const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+  const unsigned hmask = (unsigned)p.Hcap - 1u, bmask = (unsigned)p.Bwords - 1u;
+  const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
+  const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
+  const unsigned* bloom = d.bloom + (size_t)lane_b * p.Bwords;
+  // knn_out still holds this frame's first-iteration neighbours (k_predict starts every frame at outer_it 0)
+  const bool seed_from_prev = outer_it == 1 && !force && shard_world == 1;
+  // ---- phase 0: slot tid <-> Morton position t0 + tid
+  {
+    const int t = t0 + tid;
+    const bool mine = t < E;
+    const int e = (mine && !force) ? d.perm[(size_t)lane_b * p.Ecap + t] : t;
+    const float4 c = mine ? d.edges[(size_t)lane_b * p.Ecap + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
+    const bool searchable = mine && ws.hash_points > 0 && isfinite(qx) && isfinite(qy) && isfinite(qz);
+    unsigned occ = 0;
+    uint2 sc = make_uint2(0u, 0u);
+    float ub = 3.0e38f;
+    if (searchable) {
+      const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
+#pragma unroll
+      for (int r = 0; r < 9; ++r) occ |= bloom_row(bloom, bmask, cx - 1, 3, cy + r % 3 - 1, cz + r / 3 - 1) << (3 * r);
+      sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
+      occ = (occ & ~(1u << 13)) | 0x80000000u;
+      // Second outer iteration (src/laser_odometry.cc:198): the map is the same as in the first and the pose moved
+      // by millimetres, so the five neighbours found then are five map points close to this query: the largest of
+      // their distances bounds the 5th-best distance from above.  It only prunes (cells and candidates with
+      // d2 > ub); the search stays exact.
+      if (seed_from_prev) {
+        const int* prev = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+        if (prev[0] >= 0) {
+          const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
+          float m = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const float4 pt = lin[prev[r]];
+            const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
+            m = fmaxf(m, __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
+          }
+          if (m == m) ub = m;   // not NaN
+        }
+      }
+    }
+    sm.qx[tid] = qx; sm.qy[tid] = qy; sm.qz[tid] = qz; sm.occ[tid] = occ; sm.ub[tid] = ub;
+    sm.own_start[tid] = sc.x; sm.own_cnt[tid] = sc.y; sm.edge[tid] = mine ? e : -1;
+    cta_sort_by_key(sm, tid, min(63u, (sc.y + 3u) >> 2));
+  }
+  // ---- phase 1: own bucket, then list the neighbour buckets
+  {
+    const int u = sm.perm[tid];
+    const float qx = sm.qx[u], qy = sm.qy[u], qz = sm.qz[u];
+    const unsigned occ = sm.occ[u];
+    const float ub = sm.ub[u];
+    Knn5 k;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) k.k[r] = kEmptyCand;
+    unsigned work = 0;
+    int nseg = 0;
+    if (occ >> 31) {
+      knn_scan_bucket(sorted + sm.own_start[u], sm.own_cnt[u], qx, qy, qz, ub, k);
+      const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
+      // every lane walks ITS occupied cells (set bits of the cube's occupancy); the bound is fixed while listing, so
+      // the visiting order does not matter
+      for (unsigned rest = occ & 0x7ffffffu; rest; rest &= rest - 1u) {
+        const int b = __ffs(rest) - 1;
+        const int dz = b / 9 - 1, r9 = b - 9 * (dz + 1), dy = r9 / 3 - 1, dx = r9 - 3 * (dy + 1) - 1;
+        const float dmin = cell_min_d2(qx, qy, qz, cx + dx, cy + dy, cz + dz);
+        if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) continue;
+        const uint2 sc = hash_lookup(tab, hmask, gen, cx + dx, cy + dy, cz + dz);
+        if (sc.y == 0u) continue;
+        if (nseg < kSegCap) { sm.seg[nseg][u] = sc; ++nseg; work += sc.y; }
+        else knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, ub, k);   // list full: scan in place
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) sm.k[r][u] = k.k[r];
+    sm.nseg[u] = (unsigned char)nseg;
+    cta_sort_by_key(sm, u, min(63u, (work + 7u) >> 3));
+  }
+  // ---- phase 2: flattened scan of the listed buckets, fallback, output
+  const int v = sm.perm[tid];
+  const float qx = sm.qx[v], qy = sm.qy[v], qz = sm.qz[v];
+  const bool searchable = (sm.occ[v] >> 31) != 0;
+  const float ub = sm.ub[v];
+  const int e = sm.edge[v];
+  Knn5 k;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) k.k[r] = sm.k[r][v];
+  {
+    const int nseg = sm.nseg[v];
+    int si = 0;
+    unsigned j = 0, jend = 0;
+    for (;;) {
+      if (j == jend && si < nseg) { const uint2 sg = sm.seg[si++][v]; j = sg.x; jend = sg.x + sg.y; }
+      const bool scanning = j != jend;
+      if (!__any_sync(0xffffffffu, scanning)) break;
+      if (scanning) {
+        const unsigned last = jend - 1u, n = jend - j;
+        const float4 p0 = __ldg(sorted + j), p1 = __ldg(sorted + min(j + 1u, last));
+        const float4 p2 = __ldg(sorted + min(j + 2u, last)), p3 = __ldg(sorted + min(j + 3u, last));
+        knn_offer(p0, qx, qy, qz, ub, k);
+        if (n > 1u) knn_offer(p1, qx, qy, qz, ub, k);
+        if (n > 2u) knn_offer(p2, qx, qy, qz, ub, k);
+        if (n > 3u) knn_offer(p3, qx, qy, qz, ub, k);
+        j += min(n, 4u);
+      }
+    }
+  }
+  knn_fallback_warp(tab, sorted, bloom, hmask, bmask, gen, searchable, qx, qy, qz, cell_of(qx), cell_of(qy), cell_of(qz), k, ln);
+  if (e >= 0) {
+    int* nn_out = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) nn_out[r] = k.k[4] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+    if (d.gate) {
+      const size_t o = (size_t)lane_b * p.Ecap + e;
+      for (int r = 0; r < 5; ++r) {
+        d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+        d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
+      }
+      d.q_world[o] = make_float4(qx, qy, qz, d.edges[(size_t)lane_b * p.Ecap + e].w);
+    }
+  }
 }
 
 // The gate of every edge after a G == 1 search, one thread per edge in edge order (the edge-sharded mode: this
@@ -778,7 +982,12 @@ static void launch_associate_any(const DevBuffers& d, cudaStream_t s, int lane0,
   else if (G == 8) k_associate<8><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
   else if (G == 4) k_associate<4><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
   else {
-    k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+    // LIODOM_ASSOC_CTA=1: the CTA-level, work-balanced variant (parity-green, measured 5 % slower at 128 lanes: its
+    // list insertions run with 5 of 32 lanes and its barriers cost occupancy; profiles/k_associate_cta_r02d_lanes128.txt)
+    const char* cta_env = getenv("LIODOM_ASSOC_CTA");
+    const bool per_thread = !(cta_env && atoi(cta_env) == 1);
+    if (per_thread) k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+    else k_associate_cta<<<dim3((edges_per_lane + kCtaQ - 1) / kCtaQ, nlanes), kCtaQ, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
     k_line_gate<<<dim3((edges_per_lane + 127) / 128, nlanes), 128, 0, s>>>(d, lane0, outer_it, force, rank, world);
   }
 }

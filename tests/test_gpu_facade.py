@@ -33,7 +33,7 @@ def test_facade_threads_match_cabi_and_oracle(cuda_lib, tmp_path):
     assert len(rows) == len(scans) and all(len(r.split()) == 12 for r in rows)
     assert np.allclose(np.array(rows[-1].split(), float), poses[-1][:3].reshape(-1), rtol=1e-5, atol=1e-5)   # 6 significant digits
     assert open(d + "nfeats.txt").read().split() == [str(int(n)) for n in nfeats]
-    assert len(open(d + "laser_odom_times.txt").read().split()) == len(scans) - 1    # the first frame is not timed
+    assert len(open(d + "laser_odom_times.txt").read().split()) == len(scans)        # every frame, the first one too (src/laser_odometry.cc:130-134)
     for fn in ("feat_ext_times.txt", "frame_times.txt"):
         vals = open(d + fn).read().split()
         assert len(vals) == len(scans) and all(float(v) == int(float(v)) for v in vals)   # whole milliseconds

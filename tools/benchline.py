@@ -1,2 +1,2 @@
 import sys,json
-d=json.loads(sys.stdin.readline()); print(d["value"], d["e2e"]["value"], d["stages"]["ms_per_step"])
+d=json.loads(sys.stdin.readline()); print(d["value"], d["e2e"]["value"], d.get("stages",{}).get("ms_per_step"), "frac", d.get("roofline",{}).get("frac"))

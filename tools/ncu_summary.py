@@ -57,5 +57,45 @@ def kernel(path):
             print("%-86s %-16s %s" % (w, units[i], " ".join(r[i] for r in data)))
 
 
+STEP_KEYS = [("gpu__time_duration.sum", "time_us"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+             ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "dram_rd_MB"), ("dram__bytes_write.sum", "dram_wr_MB"),
+             ("lts__t_sector_hit_rate.pct", "l2_hit%"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
+             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
+             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("smsp__inst_executed.sum", "warp_inst")]
+
+
+def step(path):
+    """One row per captured launch: the whole step at a glance (every kernel of liodom_scan_batch)."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki = hdr.index("Kernel Name")
+    keys = [(k, n) for k, n in STEP_KEYS if k in hdr]
+    print("# ncu --set full --clock-control none: %s (cold cache, serialised: compare shares, not absolutes)" % path)
+    print("%-20s" % "kernel" + " ".join("%11s" % n for _, n in keys))
+    tot = 0.0
+    for r in data:
+        name = r[ki].split("(")[0].replace("void ", "")
+        vals = []
+        for k, _ in keys:
+            v = r[hdr.index(k)].replace(",", "")
+            try:
+                f = float(v)
+                if k == "gpu__time_duration.sum":
+                    f = f / 1e3 if units[hdr.index(k)] in ("ns", "nsecond") else f
+                    tot += f
+                if units[hdr.index(k)] == "byte":
+                    f /= 1e6
+                if units[hdr.index(k)] == "Kbyte":
+                    f /= 1e3
+                if units[hdr.index(k)] == "Gbyte":
+                    f *= 1e3
+                vals.append("%11.2f" % f if f < 1e7 else "%11.4g" % f)
+            except ValueError:
+                vals.append("%11s" % v[:11])
+        print("%-20s" % name[:20] + " ".join(vals))
+    print("# total %.1f us over %d launches" % (tot, len(data)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "step": step}[sys.argv[1]](sys.argv[2])
