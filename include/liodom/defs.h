@@ -25,6 +25,7 @@
 #include <Eigen/Geometry>
 #include <ros/ros.h>
 #include <std_msgs/Header.h>
+#include <sensor_msgs/PointCloud2.h>
 namespace liodom {
 typedef pcl::PointXYZI Point;
 typedef pcl::PointCloud<Point> PointCloud;
@@ -34,6 +35,11 @@ typedef Eigen::Quaterniond Quaterniond;
 typedef Eigen::Matrix4d Matrix4d;
 typedef std_msgs::Header Header;
 typedef ros::NodeHandle NodeHandle;
+typedef sensor_msgs::PointCloud2 PointCloud2;
+typedef sensor_msgs::PointField PointField;
+namespace detail {
+inline void set_stamp(Header& h, double t) { h.stamp.fromSec(t); }
+}
 }  // namespace liodom
 #else
 
@@ -100,8 +106,10 @@ struct PointCloud {     // the part of pcl::PointCloud<PointXYZI> the reference 
   }
 };
 
-struct Quaterniond {     // Eigen::Quaterniond accessors
+struct Quaterniond {     // Eigen::Quaterniond: (w, x, y, z) constructor and accessors
   double qx = 0, qy = 0, qz = 0, qw = 1;
+  Quaterniond() {}
+  Quaterniond(double w, double x, double y, double z) : qx(x), qy(y), qz(z), qw(w) {}
   double x() const { return qx; } double y() const { return qy; } double z() const { return qz; } double w() const { return qw; }
 };
 
@@ -135,17 +143,6 @@ struct Isometry3d {      // the part of Eigen::Isometry3d the reference uses
 
 /* Parameter source standing in for ros::NodeHandle's private-parameter lookup
  * (nh.param(name, out, default), src/params.cc:40-108). */
-/* nav_msgs/Odometry + geometry_msgs/TwistStamped content filled by LaserOdometer::publishOdom
- * (src/laser_odometry.cc:395-446); the TF broadcast carries the same position / orientation. */
-struct Odometry {
-  Header header;               // frame_id = fixed_frame, stamp = the scan's
-  std::string child_frame_id;  // base_frame
-  Quaterniond orientation;     // of base_link in the fixed frame
-  double position[3] = {0, 0, 0};
-  double twist_linear[3] = {0, 0, 0};
-  double twist_angular[3] = {0, 0, 0};
-};
-
 class NodeHandle {
  public:
   NodeHandle() {}
@@ -173,6 +170,34 @@ class NodeHandle {
   std::map<std::string, std::string> kv_;
 };
 
+namespace detail {
+inline void set_stamp(Header& h, double t) { h.stamp.secs = t; }
+}
 }  // namespace liodom
 #endif  // LIODOM_FACADE_USE_PCL
+
+namespace liodom {
+
+/* nav_msgs/Odometry + geometry_msgs/TwistStamped content filled by LaserOdometer::publishOdom
+ * (src/laser_odometry.cc:395-446); the TF broadcast carries the same position / orientation. */
+struct Odometry {
+  Header header;               // frame_id = fixed_frame, stamp = the scan's
+  std::string child_frame_id;  // base_frame
+  Quaterniond orientation;     // of base_link in the fixed frame
+  double position[3] = {0, 0, 0};
+  double twist_linear[3] = {0, 0, 0};
+  double twist_angular[3] = {0, 0, 0};
+};
+
+/* Only the API common to the stand-ins and to Eigen is used on poses: matrix()(i, j), Identity(), operator*. */
+namespace detail {
+inline void pose_to16(const Isometry3d& T, double* m) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) m[i * 4 + j] = T.matrix()(i, j); }
+inline Isometry3d pose_from16(const double* m) {
+  Isometry3d T = Isometry3d::Identity();
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) T.matrix()(i, j) = m[i * 4 + j];
+  return T;
+}
+}  // namespace detail
+
+}  // namespace liodom
 #endif  // INCLUDE_LIODOM_DEFS_H

@@ -7,6 +7,16 @@
 
 #include <atomic>
 #include <functional>
+#include <thread>
+
+#ifdef LIODOM_FACADE_USE_PCL
+// the third-party headers the reference's feature_extractor.h pulls in (include/liodom/feature_extractor.h:24-34);
+// src/liodom_node.cc relies on them transitively (pcl::fromROSMsg, sensor_msgs::PointCloud2ConstPtr)
+#include <omp.h>
+#include <pcl_conversions/pcl_conversions.h>
+#include <ros/ros.h>
+#include <sensor_msgs/PointCloud2.h>
+#endif
 
 #include <liodom/params.h>
 #include <liodom/shared_data.h>
@@ -21,10 +31,12 @@ namespace liodom {
  * count 1) for liodom::Point = PointXYZI.  False when x, y or z has no match or the message is
  * big-endian; a missing intensity gives off_intensity = -1 (the field stays 0, PCL only warns). */
 bool cloudLayoutFromFields(const PointCloud2& msg, liodom_cloud_layout* layout);
+#ifndef LIODOM_FACADE_USE_PCL   // with PCL present pcl::fromROSMsg is used as the reference does
 /* Host-side pcl::fromROSMsg (used for the small received local map, mapClb src/liodom_node.cc:57-64). */
 bool fromROSMsg(const PointCloud2& msg, PointCloud& cloud);
 /* lidarClb's conversion (src/liodom_node.cc:40-44) without touching the points: keeps the message. */
 bool fromROSMsgDeferred(const PointCloud2::ConstPtr& msg, PointCloud& cloud);
+#endif
 
 class FeatureExtractor {
  public:
@@ -43,6 +55,9 @@ class FeatureExtractor {
 
  private:
   NodeHandle nh_;
+#ifdef LIODOM_FACADE_USE_PCL
+  ros::Publisher pc_edges_pub_;   // "edges", published from inside the worker as the reference does (src/feature_extractor.cc:36, :71-74)
+#endif
   SharedData* sdata;
   Stats* stats;
   Params* params;

@@ -7,6 +7,18 @@
 
 #include <atomic>
 #include <functional>
+#include <thread>
+
+#ifdef LIODOM_FACADE_USE_PCL
+// ROS / tf / message headers of the reference's laser_odometry.h (include/liodom/laser_odometry.h:33-50)
+#include <ros/ros.h>
+#include <nav_msgs/Odometry.h>
+#include <geometry_msgs/TwistStamped.h>
+#include <tf/transform_datatypes.h>
+#include <tf/transform_listener.h>
+#include <tf/transform_broadcaster.h>
+#include <pcl_conversions/pcl_conversions.h>
+#endif
 
 #include <liodom/params.h>
 #include <liodom/shared_data.h>
@@ -55,6 +67,11 @@ class LaserOdometer {
 
  private:
   NodeHandle nh_;
+#ifdef LIODOM_FACADE_USE_PCL
+  ros::Publisher odom_pub_, twist_pub_;            // published from inside the worker (src/laser_odometry.cc:93-94, :395-446)
+  tf::TransformBroadcaster tf_broadcaster_;
+  bool getBaseToLaserTf(const std::string& frame_id);   // src/laser_odometry.cc:368-393
+#endif
   bool init_;
   Isometry3d odom_;
   SharedData* sdata;
@@ -65,6 +82,15 @@ class LaserOdometer {
   std::function<void(const Odometry&)> odom_msg_cb_;
   Isometry3d prev_odom_, laser_to_base_;
   double prev_stamp_ = 0.0;
+  // output-rate watchdog (src/laser_odometry.cc:239-256): 5-sample moving means of the input / output frequency
+  double in_freqs_[5], out_freqs_[5], mean_in_freq_ = 100.0, mean_out_freq_ = 100.0;
+  int num_freqs_ = 0;
+  double last_in_time_secs_ = 0.0, last_out_time_secs_ = 0.0;
+  long rate_warnings_ = 0;
+  void watchdog(double stamp_secs);
+ public:
+  long rateWarnings() const { return rate_warnings_; }   // how often "Output frequency too low" fired (the reference only logs it)
+ private:
   bool ensureContext();
   void publishOdom(const Header& header, const Isometry3d& pose);
 };

@@ -35,7 +35,7 @@ class Params {
   void operator=(Params const&) = delete;
 
  protected:
-  Params() { readParams(NodeHandle()); }
+  Params();   // the reference's defaults (src/params.cc:40-108); readParams overrides them
   ~Params() {}
 
  private:

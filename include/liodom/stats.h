@@ -5,8 +5,12 @@
 #ifndef INCLUDE_LIODOM_STATS_H
 #define INCLUDE_LIODOM_STATS_H
 
+// the same standard headers as the reference's stats.h (include/liodom/stats.h:24-30): src/liodom_node.cc uses std::cout through them
+#include <fstream>
+#include <iostream>
 #include <mutex>
 #include <queue>
+#include <sstream>
 #include <string>
 #include <vector>
 

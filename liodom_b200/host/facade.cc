@@ -34,6 +34,11 @@ Params* Params::getInstance() {
   return instance_;
 }
 
+Params::Params()
+    : min_range_(3.0), max_range_(75.0), lidar_type_(0), scan_lines_(64), scan_regions_(8), edges_per_region_(10),
+      min_points_per_scan_(90), local_map_size_(5), use_imu_(false), filter_local_map_(false), mapping_(false),
+      save_results_(false), publish_tf_(true), results_dir_("~/"), fixed_frame_("odom"), base_frame_("base_link"), laser_frame_("") {}
+
 void Params::readParams(const NodeHandle& nh) {
   nh.param("min_range", min_range_, 3.0);
   nh.param("max_range", max_range_, 75.0);
@@ -43,10 +48,10 @@ void Params::readParams(const NodeHandle& nh) {
   nh.param("edges_per_region", edges_per_region_, 10);
   min_points_per_scan_ = (size_t)(scan_regions_ * edges_per_region_ + 10);
   nh.param("save_results", save_results_, false);
-  nh.param("save_results_dir", results_dir_, std::string("~/"));
-  nh.param("fixed_frame", fixed_frame_, std::string("odom"));
-  nh.param("base_frame", base_frame_, std::string("base_link"));
-  nh.param("laser_frame", laser_frame_, std::string(""));
+  nh.param<std::string>("save_results_dir", results_dir_, "~/");
+  nh.param<std::string>("fixed_frame", fixed_frame_, "odom");
+  nh.param<std::string>("base_frame", base_frame_, "base_link");
+  nh.param<std::string>("laser_frame", laser_frame_, "");
   int pframes = 5;
   nh.param("prev_frames", pframes, 5);
   local_map_size_ = (size_t)pframes;
@@ -193,9 +198,17 @@ static void xyzi_from_cloud(const PointCloud& pc, std::vector<float>* out) {
 // FeatureExtractor (src/feature_extractor.cc:24-82)
 // ---------------------------------------------------------------------------------------------
 FeatureExtractor::FeatureExtractor(const NodeHandle& nh)
-    : nh_(nh), sdata(SharedData::getInstance()), stats(Stats::getInstance()), params(Params::getInstance()) {}
+    : nh_(nh), sdata(SharedData::getInstance()), stats(Stats::getInstance()), params(Params::getInstance()) {
+#ifdef LIODOM_FACADE_USE_PCL
+  pc_edges_pub_ = nh_.advertise<sensor_msgs::PointCloud2>("edges", 10);
+#endif
+}
 FeatureExtractor::FeatureExtractor(const FeatureExtractor& o)
-    : nh_(o.nh_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), edges_cb_(o.edges_cb_), ctx_points_(o.ctx_points_) {}
+    : nh_(o.nh_),
+#ifdef LIODOM_FACADE_USE_PCL
+      pc_edges_pub_(o.pc_edges_pub_),
+#endif
+      sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), edges_cb_(o.edges_cb_), ctx_points_(o.ctx_points_) {}
 FeatureExtractor::~FeatureExtractor() {}
 
 bool FeatureExtractor::ensureContext(size_t npoints) {
@@ -222,6 +235,7 @@ bool cloudLayoutFromFields(const PointCloud2& msg, liodom_cloud_layout* layout) 
   return true;
 }
 
+#ifndef LIODOM_FACADE_USE_PCL   // with PCL present pcl::fromROSMsg does this (src/liodom_node.cc:43-44)
 bool fromROSMsg(const PointCloud2& msg, PointCloud& cloud) {
   liodom_cloud_layout lay;
   cloud.clear(); cloud.raw.reset();
@@ -248,6 +262,7 @@ bool fromROSMsgDeferred(const PointCloud2::ConstPtr& msg, PointCloud& cloud) {
   cloud.width = msg->width; cloud.height = msg->height; cloud.is_dense = msg->is_dense; cloud.header = msg->header;
   return true;
 }
+#endif
 
 bool FeatureExtractor::extract(const PointCloud::Ptr& pc_curr, PointCloud::Ptr& pc_edges) {
   if (!ensureContext(pc_curr->size())) return false;
@@ -256,12 +271,14 @@ bool FeatureExtractor::extract(const PointCloud::Ptr& pc_curr, PointCloud::Ptr& 
   int ne = 0;
   const int w = params->lidar_type_ == 1 ? (int)pc_curr->width : 0, h = params->lidar_type_ == 1 ? (int)pc_curr->height : 0;
   int rc;
+#ifndef LIODOM_FACADE_USE_PCL
   if (pc_curr->raw) {   // message bytes straight to the device (no host-side decode)
     liodom_cloud_layout lay;
     if (!cloudLayoutFromFields(*pc_curr->raw, &lay)) { LIODOM_ERROR("extract: unusable PointCloud2 field list"); return false; }
     const int ww = (w > 0 || lay.row_step) ? (int)pc_curr->raw->width : 0, hh = (h > 0 || lay.row_step) ? (int)pc_curr->raw->height : 0;
     rc = liodom_extract_layout(ctx_.get(), 0, pc_curr->raw->data.data(), (int)pc_curr->size(), &lay, ww, hh, edges.data(), &ne, nullptr, nullptr);
   } else
+#endif
     rc = liodom_extract(ctx_.get(), 0, pc_curr->points.data(), (int)pc_curr->size(), (int)sizeof(Point), w, h,
                         edges.data(), &ne, nullptr, nullptr, nullptr);
   if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_extract failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
@@ -282,6 +299,14 @@ void FeatureExtractor::operator()(std::atomic<bool>& running) {
       const auto end_t = Clock::now();
       stats->addFeatureExtractionTime(start_t, end_t);
       stats->addNumOfFeats(pc_edges->size());
+#ifdef LIODOM_FACADE_USE_PCL
+      {   // publishing detected edges (src/feature_extractor.cc:71-74)
+        sensor_msgs::PointCloud2 edges_msg;
+        pcl::toROSMsg(*pc_edges, edges_msg);
+        edges_msg.header = pc_header;
+        pc_edges_pub_.publish(edges_msg);
+      }
+#endif
       if (edges_cb_) edges_cb_(pc_header, pc_edges);
       sdata->pushFeatures(pc_edges, pc_header);
     }
@@ -331,18 +356,35 @@ void LocalMapManager::setMaxFrames(const size_t max_nframes) {
 // ---------------------------------------------------------------------------------------------
 // LaserOdometer (src/laser_odometry.cc:71-272)
 // ---------------------------------------------------------------------------------------------
+static double wall_now_secs() { return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count(); }
+
 LaserOdometer::LaserOdometer(const NodeHandle& nh)
     : nh_(nh), init_(false), odom_(Isometry3d::Identity()), sdata(SharedData::getInstance()), stats(Stats::getInstance()),
-      params(Params::getInstance()) {}
+      params(Params::getInstance()), prev_odom_(Isometry3d::Identity()), laser_to_base_(Isometry3d::Identity()) {
+  for (int i = 0; i < 5; ++i) { in_freqs_[i] = 20.0; out_freqs_[i] = 20.0; }   // 100 / 5 (src/laser_odometry.cc:83-90)
+  last_in_time_secs_ = last_out_time_secs_ = wall_now_secs();
+#ifdef LIODOM_FACADE_USE_PCL
+  odom_pub_ = nh_.advertise<nav_msgs::Odometry>("odom", 10);
+  twist_pub_ = nh_.advertise<geometry_msgs::TwistStamped>("twist", 10);
+#endif
+}
 LaserOdometer::LaserOdometer(const LaserOdometer& o)
-    : nh_(o.nh_), init_(o.init_), odom_(o.odom_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), odom_cb_(o.odom_cb_),
-      odom_msg_cb_(o.odom_msg_cb_), prev_odom_(o.prev_odom_), laser_to_base_(o.laser_to_base_), prev_stamp_(o.prev_stamp_) {}
+    : nh_(o.nh_),
+#ifdef LIODOM_FACADE_USE_PCL
+      odom_pub_(o.odom_pub_), twist_pub_(o.twist_pub_), tf_broadcaster_(o.tf_broadcaster_),
+#endif
+      init_(o.init_), odom_(o.odom_), sdata(o.sdata), stats(o.stats), params(o.params), ctx_(o.ctx_), odom_cb_(o.odom_cb_),
+      odom_msg_cb_(o.odom_msg_cb_), prev_odom_(o.prev_odom_), laser_to_base_(o.laser_to_base_), prev_stamp_(o.prev_stamp_),
+      mean_in_freq_(o.mean_in_freq_), mean_out_freq_(o.mean_out_freq_), num_freqs_(o.num_freqs_),
+      last_in_time_secs_(o.last_in_time_secs_), last_out_time_secs_(o.last_out_time_secs_), rate_warnings_(o.rate_warnings_) {
+  for (int i = 0; i < 5; ++i) { in_freqs_[i] = o.in_freqs_[i]; out_freqs_[i] = o.out_freqs_[i]; }
+}
 LaserOdometer::~LaserOdometer() {}
 
 bool LaserOdometer::ensureContext() {
   if (ctx_) return true;
   ctx_ = make_ctx(params, 2048, (int)params->local_map_size_, 0);   // 0: the library default capacity for the received map
-  if (ctx_) liodom_odom_set_laser_to_base(ctx_.get(), 0, laser_to_base_.matrix().m);
+  if (ctx_) { double l2b[16]; detail::pose_to16(laser_to_base_, l2b); liodom_odom_set_laser_to_base(ctx_.get(), 0, l2b); }
   return (bool)ctx_;
 }
 
@@ -370,7 +412,7 @@ bool LaserOdometer::process(const PointCloud::Ptr& feats, const Header& header, 
   const int rc = liodom_register(ctx_.get(), 0, buf.data(), (int)feats->size(), pose16, &diag);
   if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_register failed (%d): %s", rc, liodom_last_error(ctx_.get())); return false; }
   if (init_) prev_odom_ = odom_;   // prev_odom_ = odom_ before the prediction (src/laser_odometry.cc:149)
-  std::memcpy(odom_.matrix().m, pose16, sizeof(pose16));
+  odom_ = detail::pose_from16(pose16);
   init_ = true;
   LIODOM_INFO("frame %u: %d edges, map %d, matches %d/%d", header.seq, diag.n_edges, diag.n_map[0], diag.n_matches[0], diag.n_matches[1]);
   if (pose_out) *pose_out = odom_;
@@ -380,14 +422,16 @@ bool LaserOdometer::process(const PointCloud::Ptr& feats, const Header& header, 
 void LaserOdometer::setLaserToBase(const Isometry3d& laser_to_base) {
   laser_to_base_ = laser_to_base;
   if (ensureContext()) {
-    const int rc = liodom_odom_set_laser_to_base(ctx_.get(), 0, laser_to_base.matrix().m);
+    double l2b[16];
+    detail::pose_to16(laser_to_base, l2b);
+    const int rc = liodom_odom_set_laser_to_base(ctx_.get(), 0, l2b);
     if (rc != LIODOM_OK) LIODOM_ERROR("liodom_odom_set_laser_to_base failed (%d): %s", rc, liodom_last_error(ctx_.get()));
   }
 }
 
 // Eigen::Quaterniond(Matrix3d): trace / largest-diagonal branches
-static Quaterniond quat_from_rotation(const Isometry3d& T) {
-  Quaterniond q;
+static Quaterniond quat_from_rotation(const Isometry3d& Tiso) {
+  const auto& T = Tiso.matrix();
   const double tr = T(0, 0) + T(1, 1) + T(2, 2);
   double v[4];
   if (tr > 0.0) {
@@ -403,8 +447,7 @@ static Quaterniond quat_from_rotation(const Isometry3d& T) {
     v[i] = 0.5 * t; t = 0.5 / t;
     v[3] = (T(k, j) - T(j, k)) * t; v[j] = (T(j, i) + T(i, j)) * t; v[k] = (T(k, i) + T(i, k)) * t;
   }
-  q.qx = v[0]; q.qy = v[1]; q.qz = v[2]; q.qw = v[3];
-  return q;
+  return Quaterniond(v[3], v[0], v[1], v[2]);   // Eigen's (w, x, y, z) constructor
 }
 
 // tf::Matrix3x3(tf::Quaternion).getRPY (getEulerYPR, solution 1)
@@ -436,10 +479,10 @@ Odometry LaserOdometer::makeOdometry(const Header& header, const Isometry3d& pos
   msg.child_frame_id = base_frame;
   const Isometry3d odom_base_link = pose * laser_to_base;   // transform to base_link before publication
   msg.orientation = quat_from_rotation(odom_base_link);
-  for (int k = 0; k < 3; ++k) msg.position[k] = odom_base_link(k, 3);
+  for (int k = 0; k < 3; ++k) msg.position[k] = odom_base_link.matrix()(k, 3);
   const double delta_time = header.stamp.toSec() - prev_stamp;
   const Isometry3d delta_odom = (prev_odom * laser_to_base).inverse() * odom_base_link;
-  for (int k = 0; k < 3; ++k) msg.twist_linear[k] = delta_odom(k, 3) / delta_time;
+  for (int k = 0; k < 3; ++k) msg.twist_linear[k] = delta_odom.matrix()(k, 3) / delta_time;
   double roll, pitch, yaw;
   rpy_from_quat(quat_from_rotation(delta_odom), &roll, &pitch, &yaw);
   msg.twist_angular[0] = roll / delta_time; msg.twist_angular[1] = pitch / delta_time; msg.twist_angular[2] = yaw / delta_time;
@@ -447,8 +490,78 @@ Odometry LaserOdometer::makeOdometry(const Header& header, const Isometry3d& pos
 }
 
 void LaserOdometer::publishOdom(const Header& header, const Isometry3d& pose) {
-  if (odom_msg_cb_) odom_msg_cb_(makeOdometry(header, pose, prev_odom_, laser_to_base_, prev_stamp_, params->fixed_frame_, params->base_frame_));
+  const Odometry m = makeOdometry(header, pose, prev_odom_, laser_to_base_, prev_stamp_, params->fixed_frame_, params->base_frame_);
+#ifdef LIODOM_FACADE_USE_PCL
+  {   // src/laser_odometry.cc:395-446: nav_msgs/Odometry, geometry_msgs/TwistStamped and the TF, from inside the worker
+    nav_msgs::Odometry laser_odom_msg;
+    laser_odom_msg.header.frame_id = params->fixed_frame_;
+    laser_odom_msg.child_frame_id = params->base_frame_;
+    laser_odom_msg.header.stamp = header.stamp;
+    laser_odom_msg.pose.pose.orientation.x = m.orientation.x(); laser_odom_msg.pose.pose.orientation.y = m.orientation.y();
+    laser_odom_msg.pose.pose.orientation.z = m.orientation.z(); laser_odom_msg.pose.pose.orientation.w = m.orientation.w();
+    laser_odom_msg.pose.pose.position.x = m.position[0]; laser_odom_msg.pose.pose.position.y = m.position[1]; laser_odom_msg.pose.pose.position.z = m.position[2];
+    laser_odom_msg.twist.twist.linear.x = m.twist_linear[0]; laser_odom_msg.twist.twist.linear.y = m.twist_linear[1]; laser_odom_msg.twist.twist.linear.z = m.twist_linear[2];
+    laser_odom_msg.twist.twist.angular.x = m.twist_angular[0]; laser_odom_msg.twist.twist.angular.y = m.twist_angular[1]; laser_odom_msg.twist.twist.angular.z = m.twist_angular[2];
+    odom_pub_.publish(laser_odom_msg);
+    geometry_msgs::TwistStamped twist_msg;
+    twist_msg.header.frame_id = params->base_frame_;
+    twist_msg.header.stamp = header.stamp;
+    twist_msg.twist = laser_odom_msg.twist.twist;
+    twist_pub_.publish(twist_msg);
+    if (params->publish_tf_) {
+      tf::Transform transform;
+      transform.setOrigin(tf::Vector3(m.position[0], m.position[1], m.position[2]));
+      transform.setRotation(tf::Quaternion(m.orientation.x(), m.orientation.y(), m.orientation.z(), m.orientation.w()));
+      tf_broadcaster_.sendTransform(tf::StampedTransform(transform, header.stamp, params->fixed_frame_, params->base_frame_));
+    }
+  }
+#endif
+  if (odom_msg_cb_) odom_msg_cb_(m);
   prev_stamp_ = header.stamp.toSec();   // src/laser_odometry.cc:127,264
+}
+
+#ifdef LIODOM_FACADE_USE_PCL
+// src/laser_odometry.cc:368-393: the static base -> laser transform, looked up once through tf
+bool LaserOdometer::getBaseToLaserTf(const std::string& frame_id) {
+  tf::TransformListener tf_listener;
+  tf::StampedTransform laser_to_base_tf;
+  try {
+    tf_listener.waitForTransform(frame_id, params->base_frame_, ros::Time(0), ros::Duration(1.0));
+    tf_listener.lookupTransform(frame_id, params->base_frame_, ros::Time(0), laser_to_base_tf);
+  } catch (tf::TransformException& ex) {
+    LIODOM_ERROR("Could not get initial transform from base to laser frame, %s", ex.what());
+    return false;
+  }
+  const double qx = laser_to_base_tf.getRotation().x(), qy = laser_to_base_tf.getRotation().y(), qz = laser_to_base_tf.getRotation().z(), qw = laser_to_base_tf.getRotation().w();
+  double m[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1};   // Eigen::Quaterniond::toRotationMatrix
+  const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  m[0] = 1.0 - (tyy + tzz); m[1] = txy - twz; m[2] = txz + twy;
+  m[4] = txy + twz; m[5] = 1.0 - (txx + tzz); m[6] = tyz - twx;
+  m[8] = txz - twy; m[9] = tyz + twx; m[10] = 1.0 - (txx + tyy);
+  m[3] = laser_to_base_tf.getOrigin().x(); m[7] = laser_to_base_tf.getOrigin().y(); m[11] = laser_to_base_tf.getOrigin().z();
+  setLaserToBase(detail::pose_from16(m));
+  return true;
+}
+#endif
+
+// Output-rate watchdog of the reference (src/laser_odometry.cc:239-256): moving means over 5 samples of the input
+// frequency (from the scan stamps) and of the output frequency (wall clock); a warning when out < 0.8 * in.
+void LaserOdometer::watchdog(double stamp_secs) {
+  const double now_secs = wall_now_secs();
+  mean_in_freq_ -= in_freqs_[num_freqs_];
+  in_freqs_[num_freqs_] = (1.0 / (stamp_secs - last_in_time_secs_)) / 5.0;
+  mean_in_freq_ += in_freqs_[num_freqs_];
+  last_in_time_secs_ = stamp_secs;
+  mean_out_freq_ -= out_freqs_[num_freqs_];
+  out_freqs_[num_freqs_] = (1.0 / (now_secs - last_out_time_secs_)) / 5.0;
+  mean_out_freq_ += out_freqs_[num_freqs_];
+  last_out_time_secs_ = now_secs;
+  num_freqs_ = (num_freqs_ + 1) % 5;
+  if (mean_out_freq_ < mean_in_freq_ * 0.8) {
+    ++rate_warnings_;
+    LIODOM_INFO("Output frequency too low: %2.2f (in: %2.2f)", mean_out_freq_, mean_in_freq_);
+  }
 }
 
 void LaserOdometer::operator()(std::atomic<bool>& running) {
@@ -457,6 +570,12 @@ void LaserOdometer::operator()(std::atomic<bool>& running) {
     Header feat_header;
     if (sdata->popFeatures(feats, feat_header)) {
       const bool first = !init_;
+#ifdef LIODOM_FACADE_USE_PCL
+      if (first) {   // cache the static tf from base to laser (src/laser_odometry.cc:110-119)
+        if (params->laser_frame_ == "") params->laser_frame_ = feat_header.frame_id;
+        if (!getBaseToLaserTf(params->laser_frame_)) { LIODOM_ERROR("Skipping point_cloud"); return; }
+      }
+#endif
       const auto start_t = Clock::now();
       Isometry3d pose;
       const bool ok = process(feats, feat_header, &pose);
@@ -468,6 +587,7 @@ void LaserOdometer::operator()(std::atomic<bool>& running) {
         stats->stopFrame(end_t);
         // first frame: prev_stamp_ is set BEFORE publishOdom (:127), so its twist divides by zero as the reference's does
         if (first) prev_stamp_ = feat_header.stamp.toSec();
+        else watchdog(feat_header.stamp.toSec());
         if (odom_cb_) odom_cb_(feat_header, odom_);
         publishOdom(feat_header, odom_);
       }
@@ -493,7 +613,9 @@ void Map::updateMap(const PointCloud::Ptr& pc_in, const Isometry3d& pose) {
   if (!map_) return;
   std::vector<float> buf;
   xyzi_from_cloud(*pc_in, &buf);
-  const int rc = liodom_map_update(map_, buf.data(), (int)pc_in->size(), pose.matrix().m);
+  double T16[16];
+  detail::pose_to16(pose, T16);
+  const int rc = liodom_map_update(map_, buf.data(), (int)pc_in->size(), T16);
   if (rc != LIODOM_OK) LIODOM_ERROR("liodom_map_update failed (%d): %s", rc, liodom_map_last_error(map_));
 }
 PointCloud::Ptr Map::getMap() {
@@ -511,9 +633,11 @@ PointCloud::Ptr Map::getLocalMap(const Isometry3d& pose, int cells_xy, int cells
   PointCloud::Ptr out(new PointCloud);
   if (!map_) return out;
   int n = 0;
-  int rc = liodom_map_get_local(map_, pose.matrix().m, cells_xy, cells_z, nullptr, 0, &n);
+  double T16[16];
+  detail::pose_to16(pose, T16);
+  int rc = liodom_map_get_local(map_, T16, cells_xy, cells_z, nullptr, 0, &n);
   std::vector<float> buf((size_t)std::max(n, 1) * 4);
-  if (rc == LIODOM_OK && n > 0) rc = liodom_map_get_local(map_, pose.matrix().m, cells_xy, cells_z, buf.data(), n, &n);
+  if (rc == LIODOM_OK && n > 0) rc = liodom_map_get_local(map_, T16, cells_xy, cells_z, buf.data(), n, &n);
   if (rc != LIODOM_OK) { LIODOM_ERROR("liodom_map_get_local failed (%d): %s", rc, liodom_map_last_error(map_)); return out; }
   cloud_from_xyzi(buf.data(), n, out.get());
   return out;
@@ -533,6 +657,7 @@ double Map::getMapEntropy() {
 
 }  // namespace liodom
 
+#ifndef LIODOM_FACADE_USE_PCL   // with ROS present the reference's own liodom_node.cc is the harness
 // ---------------------------------------------------------------------------------------------
 // Array-driven harness standing in for liodom_node / liodom_mapping_node (src/liodom_node.cc:72-121,
 // src/liodom_mapping_node.cc:45-90): it feeds clouds through SharedData exactly like lidarClb does
@@ -571,7 +696,7 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
   std::vector<int> nf((size_t)nframes, 0);
   fext.setEdgesCallback([&](const Header& h, const PointCloud::Ptr& e) { if ((int)h.seq < nframes) nf[h.seq] = (int)e->size(); });
   lodom.setOdomCallback([&](const Header& h, const Isometry3d& pose) {
-    if ((int)h.seq < nframes && poses_out) std::memcpy(poses_out + 16 * (size_t)h.seq, pose.matrix().m, sizeof(double) * 16);
+    if ((int)h.seq < nframes && poses_out) detail::pose_to16(pose, poses_out + 16 * (size_t)h.seq);
     produced++;
   });
   std::atomic<bool> running(true);
@@ -579,7 +704,7 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
   std::thread lodom_thread(lodom, std::ref(running));
   for (int f = 0; f < nframes; ++f) {   // lidarClb (src/liodom_node.cc:40-55)
     PointCloud::Ptr pc = make_cloud(f);
-    Header h; h.seq = (uint32_t)f; h.stamp.secs = 0.1 * f; h.frame_id = "laser";
+    Header h; h.seq = (uint32_t)f; detail::set_stamp(h, 0.1 * f); h.frame_id = "laser";
     stats->startFrame(Clock::now());
     sdata->pushPointCloud(pc, h);
     if (opt->lockstep) {
@@ -624,10 +749,8 @@ int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans,
 // twist linear, twist angular.
 void liodom_host_make_odometry(const double* pose16, const double* prev_odom16, const double* l2b16, double stamp, double prev_stamp, double* out13) {
   using namespace liodom;
-  Isometry3d pose, prev, l2b;
-  std::memcpy(pose.matrix().m, pose16, sizeof(double) * 16); std::memcpy(prev.matrix().m, prev_odom16, sizeof(double) * 16);
-  std::memcpy(l2b.matrix().m, l2b16, sizeof(double) * 16);
-  Header h; h.stamp.secs = stamp;
+  const Isometry3d pose = detail::pose_from16(pose16), prev = detail::pose_from16(prev_odom16), l2b = detail::pose_from16(l2b16);
+  Header h; detail::set_stamp(h, stamp);
   const Odometry m = LaserOdometer::makeOdometry(h, pose, prev, l2b, prev_stamp, "odom", "base_link");
   out13[0] = m.orientation.x(); out13[1] = m.orientation.y(); out13[2] = m.orientation.z(); out13[3] = m.orientation.w();
   for (int k = 0; k < 3; ++k) { out13[4 + k] = m.position[k]; out13[7 + k] = m.twist_linear[k]; out13[10 + k] = m.twist_angular[k]; }
@@ -687,3 +810,4 @@ int liodom_host_run_sequence_msgs(const liodom_host_options* opt, const unsigned
 }
 
 }  // extern "C"
+#endif  // !LIODOM_FACADE_USE_PCL

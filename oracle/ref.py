@@ -21,6 +21,70 @@ _vp = ctypes.c_void_p
 _lib = None
 
 
+_DROPIN_NODE = os.path.join(_HERE, "_ref", "libliodom_dropin_node.so")
+_DROPIN_MAPPING = os.path.join(_HERE, "_ref", "libliodom_dropin_mapping.so")
+
+
+def build_dropin(force=False):
+    """The reference's node mains (src/liodom_node.cc, src/liodom_mapping_node.cc), unmodified, over THIS repo's facade
+    (needs liodom_b200/libliodom_b200.so to link).  Returns the two paths, or None when neither sources nor prebuilt
+    libraries exist."""
+    have = os.path.exists(_DROPIN_NODE) and os.path.exists(_DROPIN_MAPPING)
+    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        return (_DROPIN_NODE, _DROPIN_MAPPING) if have else None
+    args = ["make", "-C", _HERE, "dropin", "CXX=g++", "REF=" + REFERENCE_ROOT]
+    if force:
+        args.insert(1, "-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return _DROPIN_NODE, _DROPIN_MAPPING
+
+
+def dropin_available():
+    return (os.path.exists(_DROPIN_NODE) and os.path.exists(_DROPIN_MAPPING)) or os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))
+
+
+def _kv(params):
+    out = []
+    for k, v in params.items():
+        if isinstance(v, bool):
+            v = "true" if v else "false"
+        out.append("%s=%s" % (k, v))
+    return ";".join(out).encode()
+
+
+def dropin_node_run(scans, width=0, height=0, dt=0.1, **params):
+    """src/liodom_node.cc's main() (unmodified) over this repo's facade + CUDA library.
+    -> (odom [n,13]: orientation x,y,z,w, position, twist linear, twist angular; edge counts [n]; frames produced)."""
+    paths = build_dropin()
+    L = ctypes.CDLL(paths[0])
+    L.dropin_node_run.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, _vp, _vp]
+    L.dropin_set_log_level(2)
+    npts = np.array([len(s) for s in scans], np.int32)
+    pts = np.ascontiguousarray(np.concatenate(scans), dtype=np.float32)
+    odom = np.zeros((len(scans), 13))
+    ne = np.zeros(len(scans), np.int32)
+    n = L.dropin_node_run(_p(pts), _p(npts), len(scans), pts.shape[1], width, height, dt, _kv(params), _p(odom), _p(ne))
+    return odom, ne, n
+
+
+def dropin_mapping_run(clouds, poses, **params):
+    """src/liodom_mapping_node.cc's main() (unmodified) over this repo's Map facade.
+    -> (map_local sizes [n], last map_local [m,4], last map [k,4])."""
+    paths = build_dropin()
+    L = ctypes.CDLL(paths[1])
+    L.dropin_mapping_run.argtypes = [_vp, _vp, ctypes.c_int, _vp, ctypes.c_char_p, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int]
+    L.dropin_set_log_level(3)
+    npts = np.array([len(c) for c in clouds], np.int32)
+    pts = np.ascontiguousarray(np.concatenate(clouds), dtype=np.float32)
+    P = np.ascontiguousarray(np.stack(poses).reshape(-1, 16), dtype=np.float64)
+    sizes = np.zeros(len(clouds), np.int32)
+    cap = int(npts.sum()) + 16
+    loc = np.zeros((cap, 4), np.float32)
+    mp = np.zeros((cap, 4), np.float32)
+    k = L.dropin_mapping_run(_p(pts), _p(npts), len(clouds), _p(P), _kv(params), _p(sizes), _p(loc), cap, _p(mp), cap)
+    return sizes, loc[:sizes[-1]].copy(), (mp[:k].copy() if k >= 0 else None)
+
+
 def build(force=False):
     """Compile the reference's sources when they are present; otherwise keep a prebuilt library."""
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):

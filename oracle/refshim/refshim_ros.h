@@ -19,6 +19,7 @@
 #include <memory>
 #include <mutex>
 #include <queue>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -57,6 +58,20 @@ struct Bus {
   }
 };
 
+// node-level plumbing used by the unmodified src/liodom_node.cc / liodom_mapping_node.cc (drop-in build of the facade)
+struct Subscribers {
+  std::mutex mu;
+  std::map<std::string, std::function<void(const std::shared_ptr<const void>&)> > table;
+  static Subscribers& get() { static Subscribers s; return s; }
+  template <typename M> bool deliver(const std::string& topic, const std::shared_ptr<const M>& msg) {
+    std::function<void(const std::shared_ptr<const void>&)> f;
+    { std::lock_guard<std::mutex> lk(mu); auto it = table.find(topic); if (it == table.end()) return false; f = it->second; }
+    f(std::static_pointer_cast<const void>(msg));
+    return true;
+  }
+};
+struct SpinHook { std::function<void()> player; static SpinHook& get() { static SpinHook h; return h; } };
+
 struct ClockState { bool frozen = false; double now = 0.0; int log_level = 1; long warnings = 0; static ClockState& get() { static ClockState c; return c; } };
 
 }  // namespace refshim
@@ -70,11 +85,28 @@ struct ClockState { bool frozen = false; double now = 0.0; int log_level = 1; lo
 #define ROS_INFO(...) REFSHIM_LOG(2, "info", __VA_ARGS__)
 #define ROS_WARN(...) REFSHIM_LOG(3, "warn", __VA_ARGS__)
 #define ROS_ERROR(...) REFSHIM_LOG(4, "error", __VA_ARGS__)
+#define ROS_INFO_STREAM(args) do { if (2 >= refshim::ClockState::get().log_level + 2) { std::ostringstream ss_; ss_ << args; std::fprintf(stderr, "[ref info] %s\n", ss_.str().c_str()); } } while (0)
 #define ROS_ERROR_ONCE(...) do { static bool hit_ = false; if (!hit_) { hit_ = true; REFSHIM_LOG(4, "error", __VA_ARGS__); } } while (0)
 
 namespace ros {
 
-struct Duration { double d; explicit Duration(double s = 0.0) : d(s) {} double toSec() const { return d; } };
+struct Duration {
+  double d;
+  explicit Duration(double s = 0.0) : d(s) {}
+  double toSec() const { return d; }
+  bool sleep() const { std::this_thread::sleep_for(std::chrono::duration<double>(d)); return true; }
+};
+struct WallDuration { double d; explicit WallDuration(double s = 0.0) : d(s) {} double toSec() const { return d; } };
+struct WallTime {
+  double t = 0.0;
+  static WallTime now() { WallTime w; w.t = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count(); return w; }
+  WallDuration operator-(const WallTime& o) const { return WallDuration(t - o.t); }
+};
+struct WallTimerEvent {};
+struct WallTimer {};   // never fires in the shim: the harness drives the node message by message
+inline void init(int&, char**, const std::string&) {}
+inline bool ok() { return true; }
+inline void spin() { if (refshim::SpinHook::get().player) refshim::SpinHook::get().player(); }
 struct Time {
   uint32_t sec = 0, nsec = 0;
   Time() {}
@@ -94,9 +126,12 @@ class Publisher {
   explicit Publisher(const std::string& topic) : topic_(topic) {}
   template <typename M> void publish(const M& m) const { refshim::Bus::get().put(topic_, m); }
   std::string getTopic() const { return topic_; }
+  uint32_t getNumSubscribers() const { return 1; }   // someone always listens in the harness
  private:
   std::string topic_;
 };
+
+class Subscriber {};
 
 class NodeHandle {
  public:
@@ -108,7 +143,14 @@ class NodeHandle {
     parse(text, &var);
     return true;
   }
-  template <typename M> Publisher advertise(const std::string& topic, uint32_t /*queue*/) const { return Publisher(topic); }
+  template <typename M> Publisher advertise(const std::string& topic, uint32_t /*queue*/, bool /*latch*/ = false) const { return Publisher(topic); }
+  template <typename M> Subscriber subscribe(const std::string& topic, uint32_t /*queue*/, void (*fp)(const std::shared_ptr<M const>&)) const {
+    refshim::Subscribers& s = refshim::Subscribers::get();
+    std::lock_guard<std::mutex> lk(s.mu);
+    s.table[topic] = [fp](const std::shared_ptr<const void>& m) { fp(std::static_pointer_cast<const M>(m)); };
+    return Subscriber();
+  }
+  WallTimer createWallTimer(const WallDuration&, void (*)(const WallTimerEvent&)) const { return WallTimer(); }
  private:
   static bool lookup(const std::string& name, std::string* text) {
     refshim::ParamTable& t = refshim::ParamTable::get();
@@ -297,7 +339,14 @@ class TransformListener {
 
 class TransformBroadcaster {
  public:
-  void sendTransform(const StampedTransform& t) { refshim::Bus::get().put(std::string("/tf"), t); }
+  void sendTransform(const StampedTransform& t) {
+    {
+      StaticTransforms& s = StaticTransforms::get();
+      std::lock_guard<std::mutex> lk(s.mu);
+      s.table[std::make_pair(t.frame_id_, t.child_frame_id_)] = t;
+    }
+    refshim::Bus::get().put(std::string("/tf"), t);
+  }
 };
 
 }  // namespace tf
