@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-pass", action="store_true")
     ap.add_argument("--no-single-stream", action="store_true")
+    ap.add_argument("--no-xyz12", action="store_true")
     return ap.parse_args()
 
 
@@ -388,6 +389,77 @@ def run_b200(args):
     ctx.close()
     clocks = sampler.stop()
 
+    # ---------------- end to end with 12-byte points (x, y, z only) --------------------------------------------
+    # The odometry never reads intensity (include/liodom/factors.hpp:71-105; it is only carried into the published
+    # edge cloud), and the e2e leg is bound by the PCIe transfer of the scans: a front-end that hands over xyz
+    # records moves 25 % fewer bytes.  Same frames, same C ABI call (liodom_scan_batch_layout: point_step 12, no
+    # intensity field); poses must equal the 16-byte leg's.
+    xyz12 = None
+    if args.config == "c1" and not args.no_xyz12:
+        lay = api.CloudLayout(12, 0, 0, 4, 8, -1, 0)
+        h12, p12 = {}, {}
+        for f in range(P, nframes):
+            cnt = [int(npts[l % nseq][f]) for l in range(B)]
+            buf = torch.empty((sum(cnt), 3), dtype=torch.float32).pin_memory()
+            off, ptrs = 0, []
+            for l in range(B):
+                buf[off:off + cnt[l]] = torch.from_numpy(seqs[l % nseq][f][:, :3])
+                ptrs.append(buf.data_ptr() + off * 12)
+                off += cnt[l]
+            h12[f], p12[f] = buf, ptrs
+        ctx = api.Context(batch=B, device=local, **kw)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+        for f in range(P):
+            step_dev(ctx, f)
+        ctx.results()
+        for f in range(P, P + W):
+            ctx.scan_batch_layout_ptrs(p12[f], [int(npts[l % nseq][f]) for l in range(B)], lay)
+            ctx.results()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        t_wall = time.perf_counter()
+        for f in range(P + W, nframes):
+            ctx.scan_batch_layout_ptrs(p12[f], [int(npts[l % nseq][f]) for l in range(B)], lay)
+            if f > P + W:
+                ctx.results(age=1)
+        poses12, _ = ctx.results(age=0)
+        ev1.record(stream)
+        ctx.sync()
+        barrier()
+        ms12 = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t_wall) * 1e3))
+        xyz12 = {"value": round(world * B * K / (ms12 * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms12 / K, 4),
+                 "h2d_bytes_per_step": int(h2d / K * 12 / 16), "same_poses_as_16_byte_leg": bool(np.array_equal(poses12, poses_e2e)),
+                 "layout": "point_step 12: float32 x, y, z (no intensity), liodom_scan_batch_layout"}
+        ctx.close()
+        del h12, p12
+
+    # ---------------- what the host fabric gives when every rank copies at once -------------------------------
+    barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for f in probe_frames:
+        probe[:len(host_steps[f])].copy_(host_steps[f], non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_concurrent_gbps = sum(host_steps[f].numel() * 4 for f in probe_frames) / (max_over_ranks(pe0.elapsed_time(pe1)) * 1e-3) / 1e9
+
+    # ---------------- the drop-in facade, single stream (what src/liodom_node.cc drives) -----------------------
+    facade = None
+    if rank == 0 and world == 1 and not args.no_single_stream:
+        try:
+            from liodom_b200 import host_api
+            nfac = min(len(seqs[0]), 30)
+            host_api.run_sequence(seqs[0][:3], lockstep=False, prev_frames=kw["prev_frames"], width=width, height=height)   # warm-up: contexts, first kernels
+            t0f = time.perf_counter()
+            _, _, produced = host_api.run_sequence(seqs[0][:nfac], lockstep=False, prev_frames=kw["prev_frames"], width=width, height=height)
+            dtf = time.perf_counter() - t0f
+            facade = {"value": round(produced / dtf, 1), "unit": UNIT, "ms_per_scan": round(dtf / max(produced, 1) * 1e3, 3), "frames": produced,
+                      "note": "liodom::FeatureExtractor / LaserOdometer worker threads over the SharedData queues (2 ms polling sleeps as in the "
+                              "reference, src/feature_extractor.cc:80, src/laser_odometry.cc:270), host clouds in, poses out; includes thread start-up"}
+        except Exception as e:   # the facade is optional for the headline
+            facade = {"error": str(e)}
+
     # ---------------- point-sharded 1M-point stream (BASELINE config 5, second half; short, outside the headline) -----
     sharded = None
     if not args.no_sharded_block and args.config == "c1":
@@ -455,6 +527,7 @@ def run_b200(args):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                 "ms_per_step": round(e2e_ms / K, 4), "latency_ms_per_scan": round(e2e_ms / K, 4), "same_poses_as_device_leg": same,
                 "h2d_gbps_in_run": round(h2d_in_run_gbps, 1), "h2d_gbps_link_alone": round(h2d_alone_gbps, 1),
+                "h2d_gbps_per_rank_all_ranks_copying": round(h2d_concurrent_gbps, 1),
                 "bound": "PCIe H2D of the raw scans (16 B/point)" if h2d_in_run_gbps > 0.85 * h2d_alone_gbps else "kernels"},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -465,8 +538,12 @@ def run_b200(args):
     if roof is not None:
         out["roofline"] = roof
         out["stages"] = stages
+    if xyz12 is not None:
+        out["e2e_xyz12"] = xyz12
     if single is not None:
         out["single_stream"] = single
+    if facade is not None:
+        out["facade_single_stream"] = facade
     if sharded is not None:
         out["point_sharded"] = sharded
     if cpu is not None:

@@ -288,6 +288,12 @@ class Context:
         ns = (ctypes.c_int * self.batch)(*counts)
         self._ck(self.lib.liodom_scan_batch(self.h, p, ns, stride_bytes, width, height, 1 if on_device else 0))
 
+    def scan_batch_layout_ptrs(self, ptrs, counts, layout, width=0, height=0, on_device=False):
+        """liodom_scan_batch_layout with integer addresses (pinned host or device memory)."""
+        p = (_vp * self.batch)(*ptrs)
+        ns = (ctypes.c_int * self.batch)(*counts)
+        self._ck(self.lib.liodom_scan_batch_layout(self.h, p, ns, ctypes.byref(layout), width, height, 1 if on_device else 0))
+
     def results(self, age=0):
         """Poses [batch,4,4] and edge counts of the last enqueued scan (age 0) or the one before (age 1)."""
         poses = np.empty((self.batch, 16))

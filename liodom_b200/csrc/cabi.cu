@@ -799,7 +799,7 @@ static int scan_batch_impl(liodom_ctx* c, const void* const* pts, const int* n, 
     rc = ensure_dev_in(c, max_bytes); if (rc) return rc;
     // Host scans laid out back to back (a batching front-end would do that) go over PCIe as ONE copy
     // into a packed staging area; otherwise one copy per lane into fixed-pitch slots.
-    bool packed = B > 1 && (lay.step & 15) == 0 && !lay.row_step;
+    bool packed = B > 1 && (lay.step & 3) == 0 && !lay.row_step;   // 4-byte aligned records (16-byte xyzi, 32-byte PCL, 12-byte xyz)
     size_t total = 0;
     for (int l = 0; l < B && packed; ++l) {
       if (static_cast<const char*>(pts[l]) != static_cast<const char*>(pts[0]) + total) packed = false;
