@@ -116,7 +116,7 @@ static int hash_generation_guard(liodom_ctx* c, unsigned upcoming_builds) {
   std::vector<WinState> ws(c->batch);
   CK(cudaMemcpyAsync(ws.data(), d.wstate, sizeof(WinState) * c->batch, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  for (auto& w : ws) w.gen = 0;
+  for (auto& w : ws) { w.gen = 0; w.force_full = 1; w.built = 0; }
   CK(cudaMemcpyAsync(d.wstate, ws.data(), sizeof(WinState) * c->batch, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int l = 0; l < c->batch; ++l) c->launches += launch_hash_rebuild(d, c->stream, l);
@@ -213,7 +213,13 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   p.Mcap = p.Wcap + p.Rcap;
   p.vg_blocks = (P.filter_local_map && !P.mapping) ? (p.Wcap + kVgTile - 1) / kVgTile : 0;
   int h = 1024; while (h < p.Mcap + p.Mcap / 8) h <<= 1;   // load factor <= 0.89 even if every point had its own voxel; typically < 0.2
+  // The incremental hash (no mapping, no window filter) keeps emptied cells as tombstones until the next full build,
+  // which it requests at half load: twice the slots.
+  const bool incremental = !P.mapping && !P.filter_local_map;
+  if (incremental) h <<= 1;
   p.Hcap = h;
+  p.Pcap = incremental ? kPoolFactor * p.Mcap : p.Mcap;
+  { int lc = 1024; while (lc < p.Mcap) lc <<= 1; p.LinCap = lc; }
   p.Bwords = h / 2;   // 16 filter bits per hash slot: a few % false positives (each costs one extra probe, never a wrong answer)
   if (extract_smem_needed(p) > (size_t)kMaxDynSmem) {
     fail(nullptr, LIODOM_E_INVALID, "scan_lines x scan_regions x edges_per_region needs %zu bytes of shared memory per CTA (limit %d)", extract_smem_needed(p), kMaxDynSmem);
@@ -241,8 +247,11 @@ int liodom_ctx_create(const liodom_params* up, int batch, int device, liodom_ctx
   CKC(dalloc(c, &d.received, B * (size_t)(p.Rcap > 0 ? p.Rcap : 1)));
   CKC(dalloc(c, &d.wstate, B));
   CKC(dalloc(c, &d.ostate, B));
-  CKC(dalloc(c, &d.sorted, B * p.Mcap));
-  CKC(dalloc(c, &d.lin, B * p.Mcap));
+  CKC(dalloc(c, &d.sorted, B * p.Pcap));
+  CKC(dalloc(c, &d.lin, B * p.LinCap));
+  CKC(dalloc(c, &d.cap_end, B * p.Hcap));
+  CKC(dalloc(c, &d.newcnt, B * p.Hcap));
+  CKC(dalloc(c, &d.cell_base, B * p.Hcap));
   CKC(dalloc(c, &d.htab, B * p.Hcap));
   CKC(dalloc(c, &d.bloom, B * p.Bwords));
   CKC(dalloc(c, &d.owner_list, B * p.Mcap));
@@ -543,7 +552,7 @@ int liodom_lmap_clear(liodom_ctx* c, int lane) {
   CK(cudaStreamSynchronize(c->stream));
   const unsigned gen = ws.gen; const int mf = ws.max_frames, nr = ws.n_received;
   std::memset(&ws, 0, sizeof(ws));
-  ws.gen = gen; ws.max_frames = mf; ws.n_received = nr;
+  ws.gen = gen; ws.max_frames = mf; ws.n_received = nr; ws.force_full = 1;
   CK(cudaMemcpyAsync(c->d.wstate + lane, &ws, sizeof(ws), cudaMemcpyHostToDevice, c->stream));
   rc = hash_generation_guard(c, 1); if (rc) return rc;
   c->launches += launch_hash_rebuild(c->d, c->stream, lane);

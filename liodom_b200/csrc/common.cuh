@@ -28,6 +28,8 @@ constexpr unsigned kGenBits = 12;   // hash generation tag width
 constexpr unsigned kCntBits = 20;
 constexpr int kMaxDynSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 constexpr int kVgTile = 2048;       // keys per CTA of the window-filter radix sort (256 threads x 8)
+constexpr int kHashIncr = 0, kHashFullOrdered = 1, kHashFullFast = 2;
+constexpr int kPoolFactor = 16;     // bucket pool of the incremental hash, in units of Mcap (a full build uses <= 6, a scan <= 2.2)
 
 // One slot of the open-addressing voxel hash: packed cell key (generation | iz | iy | ix), first
 // point of the cell's bucket in `sorted`, and (generation << kCntBits) | points in the cell.
@@ -43,6 +45,8 @@ struct DevParams {
   int lidar_type, scan_lines, scan_regions, edges_per_region;
   int prev_frames, filter_local_map, mapping, use_imu;
   int Ncap, Ecap, Mcap, Hcap, Rcap;  // Rcap: received-map capacity
+  int Pcap;                          // points of the bucket pool `sorted` (Mcap, or a multiple of it with the incremental hash)
+  int LinCap;                        // entries of the ring `lin` (power of two >= Mcap), indexed by sequence number & (LinCap - 1)
   int slots;                         // window slabs allocated
   int chunks;                        // ceil(Ncap / kChunk)
   int batch;
@@ -76,6 +80,18 @@ struct WinState {
   int hash_points;        // points inserted in the current hash build
   int bump;               // bucket allocator
   int n_owners;           // cells created by the current hash build (entries of owner_list)
+  // ---- incremental voxel hash (register.cu): the table and the bucket pool persist across scans; a scan evicts
+  // the oldest frame's points from the heads of their buckets and appends the new frame's at the tails
+  int hmode;              // build chosen by hash_begin: kHashIncr, kHashFullOrdered or kHashFullFast
+  int force_full;         // next build must be a full one (host edited the window / tables)
+  int built;              // a full ordered build has happened since the last table reset
+  int cells_used;         // table slots claimed since the last full build (empty cells stay as tombstones)
+  int n_touched;          // cells receiving new points in this build (entries of owner_list)
+  unsigned g_next;        // sequence number of the next point entering the window
+  unsigned g_base[kMaxSlots];   // sequence number of the first point of the frame in each slab
+  int ev_slab, ev_cnt;    // frame evicted by the last commit (ev_cnt 0: none)
+  int nw_slab, nw_cnt;    // frame added by the last commit
+  unsigned nw_g;          // its first sequence number
   // logical view of the window (oldest frame first), refreshed whenever the window changes:
   int view_prefix[kMaxSlots + 1];   // first logical index of frame k
   int view_slab[kMaxSlots];         // slab holding frame k
@@ -144,8 +160,11 @@ struct DevBuffers {
   float4* received;        // [B][Rcap]
   WinState* wstate;        // [B]
   OdomState* ostate;       // [B]
-  float4* sorted;          // [B][Mcap]
-  float4* lin;             // [B][Mcap] the same points in logical (window) order
+  float4* sorted;          // [B][Pcap] bucket pool: the points of a voxel are contiguous, oldest frame first; w = sequence number
+  float4* lin;             // [B][LinCap] ring of the same points by sequence number (neighbour fetches)
+  unsigned* cap_end;       // [B][Hcap] end of the pool region reserved for the cell in each table slot
+  unsigned* newcnt;        // [B][Hcap] points of the frame being added per cell (zero between builds)
+  unsigned* cell_base;     // [B][Hcap] where this build's new points of the cell go
   HashEntry* htab;         // [B][Hcap]
   unsigned* bloom;         // [B][Bwords] occupancy filter of the hash cells: word = hash(ix >> 5, iy, iz), bit = ix & 31
   unsigned* owner_list;    // [B][Mcap] hash slots of the cells created by the current build

@@ -14,8 +14,15 @@ namespace liodom {
 // ---------------------------------------------------------------------------------------
 // window addressing
 // ---------------------------------------------------------------------------------------
-// Called by exactly one thread after the window changed: start a new hash generation.
-__device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
+// Called by exactly one thread after the window changed (win_commit) or after the host edited it (force_full):
+// refreshes the logical view and chooses how the voxel hash follows the change.
+//   kHashIncr         evict the oldest frame's points from the heads of their buckets, append the new frame's at
+//                     the tails (table, pool and occupancy filter persist; cost ~ 2 frames instead of the window)
+//   kHashFullOrdered  rebuild everything with every bucket in frame order (what kHashIncr needs to start from):
+//                     first build, host edits, pool / table / sequence-number headroom used up
+//   kHashFullFast     the three-kernel rebuild of the whole target; used when the target is replaced wholesale
+//                     every scan anyway (mapping: received map; filter_local_map: VoxelGrid of the window)
+__device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b, bool force_full = false) {
   WinState& ws = d.wstate[lane_b];
   int acc = 0;
   for (int k = 0; k < ws.nframes; ++k) {
@@ -23,14 +30,29 @@ __device__ __forceinline__ void hash_begin(const DevBuffers& d, int lane_b) {
     ws.view_slab[k] = s; ws.view_prefix[k] = acc; acc += ws.cnt[s];
   }
   ws.view_prefix[ws.nframes] = acc;
-  ws.gen = ws.gen + 1u;
-  ws.bump = 0;
-  ws.n_owners = 0;
   ws.hash_points = ws.total + (d.p.mapping ? ws.n_received : 0);
   // computeLocalMap (src/laser_odometry.cc:286): filter iff the window is full and mapping is off;
   // launch_window_filter then replaces the target (and hash_points) before the hash is built.
   ws.vg_active = (d.filtered && d.p.filter_local_map && !d.p.mapping && ws.nframes == d.p.prev_frames) ? 1 : 0;
   for (int k = 0; k < 3; ++k) { ws.vg_lo[k] = 0xffffffffu; ws.vg_hi[k] = 0u; }
+  ws.n_touched = 0;
+  const bool fast = d.p.mapping || d.p.filter_local_map;
+  // headroom one scan can need in the worst case: every touched cell moves to a region of twice its size
+  const long long need = 2ll * ((long long)ws.total + ws.nw_cnt) + 8ll * ws.nw_cnt + 64;
+  const bool incr = !fast && !force_full && !ws.force_full && ws.built && (long long)ws.bump + need < (long long)d.p.Pcap &&
+                    (long long)ws.cells_used + ws.nw_cnt < (long long)d.p.Hcap / 2 && ws.g_next < 0x70000000u;   // sequence numbers stay non-negative as int (knn_out uses -1 for "none")
+  ws.hmode = incr ? kHashIncr : (fast ? kHashFullFast : kHashFullOrdered);
+  ws.force_full = 0;
+  if (!incr) {
+    ws.gen = ws.gen + 1u;     // every entry of the table becomes stale
+    ws.bump = 0;
+    ws.n_owners = 0;
+    ws.cells_used = 0;
+    ws.built = fast ? 0 : 1;
+    // sequence numbers restart at the logical index (oldest point of the window = 0)
+    for (int k = 0; k < ws.nframes; ++k) ws.g_base[ws.view_slab[k]] = (unsigned)ws.view_prefix[k];
+    ws.g_next = (unsigned)acc;
+  }
 }
 
 // LocalMapManager::addPointCloud bookkeeping (src/laser_odometry.cc:34-60): the new frame
@@ -39,27 +61,72 @@ __device__ __forceinline__ void win_commit(const DevBuffers& d, int lane_b, int 
   WinState& ws = d.wstate[lane_b];
   const int s = (ws.head + ws.nframes) % d.p.slots;
   ws.cnt[s] = n; ws.total += n; ws.nframes++;
+  ws.g_base[s] = ws.g_next; ws.nw_slab = s; ws.nw_cnt = n; ws.nw_g = ws.g_next;
+  ws.g_next += (unsigned)n;
+  ws.ev_cnt = 0;
   if (ws.nframes > ws.max_frames) {  // drop exactly one (the oldest) frame
+    ws.ev_slab = ws.head; ws.ev_cnt = ws.cnt[ws.head];   // its slab stays intact until the ring comes round again
     ws.total -= ws.cnt[ws.head]; ws.cnt[ws.head] = 0;
     ws.head = (ws.head + 1) % d.p.slots; ws.nframes--;
   }
 }
 
-// ---------------------------------------------------------------------------------------
-// voxel hash build: insert/count -> allocate buckets -> scatter. grid (blocks, nlanes).
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
-  const int lane_b = lane0 + blockIdx.y;
-  WinView v;
-  load_win_view(d, lane_b, &v);
+// sequence number of the oldest point of the window: logical index = sequence number - this
+__device__ __forceinline__ unsigned win_g0(const DevBuffers& d, int lane_b) {
   const WinState& ws = d.wstate[lane_b];
-  const int npts = ws.hash_points;
+  return ws.nframes > 0 ? ws.g_base[ws.head] : ws.g_next;
+}
+
+// ---------------------------------------------------------------------------------------
+// voxel hash.  Table: open addressing on packed (ix, iy, iz, generation).  Buckets: contiguous runs of the pool
+// `sorted`, the points of a voxel in frame order (oldest first), w = sequence number.  `lin`: ring of the points
+// by sequence number.  Three ways to bring it up to date after the window changed (hash_begin picks one):
+//   incremental     k_hash_evict -> k_hash_add_count -> k_hash_grow -> k_hash_add_scatter      (~2 frames of work)
+//   full, ordered   k_hash_full_ordered (one CTA per lane; rare)
+//   full, fast      k_bloom_clear -> k_hash_insert -> k_hash_alloc -> k_hash_scatter           (mapping / window filter)
+// Every kernel returns at once unless its mode is the chosen one, so the host enqueues a fixed sequence.
+// ---------------------------------------------------------------------------------------
+// Find the table slot of cell `mine` (generation-tagged key), claiming a stale slot if the cell is new.
+__device__ __forceinline__ unsigned hash_find_or_create(HashEntry* tab, unsigned mask, unsigned gen, unsigned long long mine, bool* created) {
+  unsigned slot = hash_cell(mine) & mask;
+  *created = false;
+  for (;;) {
+    unsigned long long cur = *(volatile unsigned long long*)&tab[slot].key;
+    if (cur == mine) break;
+    if ((unsigned)(cur >> 48) != gen) {  // stale generation: free
+      const unsigned long long prev = atomicCAS(&tab[slot].key, cur, mine);
+      if (prev == cur) { *created = true; break; }
+      if (prev == mine) break;
+      if ((unsigned)(prev >> 48) != gen) continue;  // lost to another stale observer; retry the slot
+    }
+    slot = (slot + 1) & mask;
+  }
+  return slot;
+}
+
+__device__ __forceinline__ void bloom_publish(const DevBuffers& d, int lane_b, const float4& pt) {
+  const int ix = cell_of(pt.x);
+  atomicOr(d.bloom + (size_t)lane_b * d.p.Bwords + bloom_word_index(ix >> 5, cell_of(pt.y), cell_of(pt.z), (unsigned)d.p.Bwords - 1u), 1u << (ix & 31));
+}
+
+__device__ __forceinline__ void hash_check_generation(const WinState& ws) {
   // The 12-bit tag only distinguishes generations because the host clears the tables and resets ws.gen before it
   // wraps (hash_generation_guard in cabi.cu).  A caller that forgot the guard must fail loudly, not reuse stale cells.
   if (ws.gen >> kGenBits) {
     if (blockIdx.x == 0 && threadIdx.x == 0) printf("liodom_b200: voxel-hash generation %u overflowed its %u-bit tag (missing hash_generation_guard)\n", ws.gen, kGenBits);
     __trap();
   }
+}
+
+// ---- full, fast ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  const WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashFullFast) return;
+  WinView v;
+  load_win_view(d, lane_b, &v);
+  const int npts = ws.hash_points;
+  hash_check_generation(ws);
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned mask = (unsigned)d.p.Hcap - 1u;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
@@ -67,28 +134,15 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
     const float4 pt = win_point(d, lane_b, v, i);
     unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
     if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { *pslot = 0xffffffffu; continue; }  // PCL kd-tree skips these
-    const unsigned long long mine = pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen);
-    unsigned slot = hash_cell(mine) & mask;
-    bool owner = false;
-    for (;;) {
-      unsigned long long cur = *(volatile unsigned long long*)&tab[slot].key;
-      if (cur == mine) break;
-      if ((unsigned)(cur >> 48) != gen) {  // stale generation: free
-        const unsigned long long prev = atomicCAS(&tab[slot].key, cur, mine);
-        if (prev == cur) { owner = true; break; }
-        if (prev == mine) break;
-        if ((unsigned)(prev >> 48) != gen) continue;  // lost to another stale observer; retry the slot
-      }
-      slot = (slot + 1) & mask;
-    }
+    bool owner;
+    const unsigned slot = hash_find_or_create(tab, mask, gen, pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen), &owner);
     if (owner) {   // first point of the cell: list it for k_hash_alloc and publish it in the occupancy filter read by k_associate
       d.owner_list[(size_t)lane_b * d.p.Mcap + atomicAdd(&d.wstate[lane_b].n_owners, 1)] = slot;
-      const int ix = cell_of(pt.x);
-      atomicOr(d.bloom + (size_t)lane_b * d.p.Bwords + bloom_word_index(ix >> 5, cell_of(pt.y), cell_of(pt.z), (unsigned)d.p.Bwords - 1u), 1u << (ix & 31));
+      bloom_publish(d, lane_b, pt);
     }
     atomicMax(&tab[slot].cnt, gen << kCntBits);
     const unsigned rank = atomicAdd(&tab[slot].cnt, 1u) & ((1u << kCntBits) - 1u);
-    *pslot = slot | (owner ? 0x80000000u : 0u);
+    *pslot = slot;
     d.pt_rank[(size_t)lane_b * d.p.Mcap + i] = rank;
   }
 }
@@ -98,6 +152,7 @@ __global__ void __launch_bounds__(256) k_hash_insert(DevBuffers d, int lane0) {
 __global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
   WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashFullFast) return;
   const int ncell = ws.n_owners, ln = threadIdx.x & 31;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   const unsigned* owners = d.owner_list + (size_t)lane_b * d.p.Mcap;
@@ -118,39 +173,225 @@ __global__ void __launch_bounds__(256) k_hash_alloc(DevBuffers d, int lane0) {
 
 __global__ void __launch_bounds__(256) k_hash_scatter(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.y;
+  const WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashFullFast) return;
   WinView v;
   load_win_view(d, lane_b, &v);
-  const int npts = d.wstate[lane_b].hash_points;
+  const int npts = ws.hash_points;
   const HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
-  float4* sorted = d.sorted + (size_t)lane_b * d.p.Mcap;
+  float4* sorted = d.sorted + (size_t)lane_b * d.p.Pcap;
+  float4* lin = d.lin + (size_t)lane_b * d.p.LinCap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
     const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
     float4 pt = win_point(d, lane_b, v, i);
-    d.lin[(size_t)lane_b * d.p.Mcap + i] = pt;
+    lin[i] = pt;                          // sequence number = logical index after a full build
     if (ps == 0xffffffffu) continue;
     pt.w = __int_as_float(i);
-    sorted[tab[ps & 0x7fffffffu].start + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
+    sorted[tab[ps].start + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
   }
 }
 
 // Clears the occupancy filters of the lanes (a kernel, not cudaMemsetAsync: a memset may be placed on a
 // copy engine, where it would wait behind the next scan's H2D transfer).
 __global__ void __launch_bounds__(256) k_bloom_clear(DevBuffers d, int lane0) {
+  if (d.wstate[lane0 + blockIdx.y].hmode != kHashFullFast) return;
   uint4* w = reinterpret_cast<uint4*>(d.bloom + (size_t)(lane0 + blockIdx.y) * d.p.Bwords);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.p.Bwords / 4; i += gridDim.x * blockDim.x) w[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// ---- incremental ---------------------------------------------------------------------------------------------
+// The evicted frame's points sit at the heads of their buckets (buckets are in frame order): advance the heads.
+__global__ void __launch_bounds__(256) k_hash_evict(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  const WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashIncr) return;
+  hash_check_generation(ws);
+  const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+  const unsigned mask = (unsigned)d.p.Hcap - 1u;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
+  const float4* slab = d.win + ((size_t)lane_b * d.p.slots + ws.ev_slab) * d.p.Ecap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ws.ev_cnt; i += gridDim.x * blockDim.x) {
+    const float4 pt = slab[i];
+    if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) continue;   // never inserted
+    const unsigned long long key = pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen);
+    unsigned slot = hash_cell(key) & mask;
+    // present by construction (the frame was inserted under this generation); a bounded walk, so that a broken
+    // invariant traps instead of hanging the device
+    unsigned probes = 0;
+    while (*(volatile unsigned long long*)&tab[slot].key != key) {
+      slot = (slot + 1) & mask;
+      if (++probes > mask) { printf("liodom_b200: evicted point has no voxel-hash cell (lane %d)\n", lane_b); __trap(); }
+    }
+    atomicAdd(&tab[slot].start, 1u);
+    atomicSub(&tab[slot].cnt, 1u);
+  }
+}
+
+// New frame, pass 1: cell of every point (created if new), rank among the frame's points of that cell.
+__global__ void __launch_bounds__(256) k_hash_add_count(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashIncr) return;
+  const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+  const unsigned mask = (unsigned)d.p.Hcap - 1u;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
+  unsigned* newcnt = d.newcnt + (size_t)lane_b * d.p.Hcap;
+  const float4* slab = d.win + ((size_t)lane_b * d.p.slots + ws.nw_slab) * d.p.Ecap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ws.nw_cnt; i += gridDim.x * blockDim.x) {
+    const float4 pt = slab[i];
+    unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
+    if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { *pslot = 0xffffffffu; continue; }
+    bool created;
+    const unsigned slot = hash_find_or_create(tab, mask, gen, pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen), &created);
+    if (created) {   // nobody reads start / cnt / cap_end of this slot before k_hash_grow
+      tab[slot].start = 0u; tab[slot].cnt = gen << kCntBits;
+      d.cap_end[(size_t)lane_b * d.p.Hcap + slot] = 0u;
+      bloom_publish(d, lane_b, pt);
+      atomicAdd(&ws.cells_used, 1);
+    }
+    const unsigned rank = atomicAdd(&newcnt[slot], 1u);
+    if (rank == 0u) d.owner_list[(size_t)lane_b * d.p.Mcap + atomicAdd(&ws.n_touched, 1)] = slot;
+    *pslot = slot;
+    d.pt_rank[(size_t)lane_b * d.p.Mcap + i] = rank;
+  }
+}
+
+// New frame, pass 2: eight threads per touched cell make room at the tail of its bucket; a bucket that has reached
+// the end of its region moves (cooperative copy) to a fresh region of twice its size.  Regions only slide forward —
+// heads advance on eviction, tails on insertion — so a steady cell moves once per ~window length of scans.
+constexpr int kGrowGroup = 8;
+__global__ void __launch_bounds__(256) k_hash_grow(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashIncr) return;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
+  unsigned* newcnt = d.newcnt + (size_t)lane_b * d.p.Hcap;
+  unsigned* cap_end = d.cap_end + (size_t)lane_b * d.p.Hcap;
+  unsigned* cell_base = d.cell_base + (size_t)lane_b * d.p.Hcap;
+  float4* sorted = d.sorted + (size_t)lane_b * d.p.Pcap;
+  const unsigned* touched = d.owner_list + (size_t)lane_b * d.p.Mcap;
+  const int ln = threadIdx.x & 31, gl = ln & (kGrowGroup - 1), leader = ln & ~(kGrowGroup - 1);
+  const unsigned gmask = ((1u << kGrowGroup) - 1u) << leader;
+  const int ngroups = gridDim.x * blockDim.x / kGrowGroup, ntouched = ws.n_touched;
+  for (int j = (blockIdx.x * blockDim.x + threadIdx.x) / kGrowGroup; j < ntouched; j += ngroups) {   // uniform over a group
+    const unsigned slot = touched[j];
+    const unsigned nc = newcnt[slot], word = tab[slot].cnt, cnt = word & ((1u << kCntBits) - 1u);
+    unsigned start = tab[slot].start;
+    if (start + cnt + nc > cap_end[slot]) {
+      const unsigned ncap = 2u * (cnt + nc) + 4u;
+      unsigned ns = 0;
+      if (gl == 0) ns = (unsigned)atomicAdd(&ws.bump, (int)ncap);   // hash_begin guarantees the headroom
+      ns = __shfl_sync(gmask, ns, leader);
+      for (unsigned k = gl; k < cnt; k += kGrowGroup) sorted[ns + k] = sorted[start + k];
+      __syncwarp(gmask);
+      if (gl == 0) { tab[slot].start = ns; cap_end[slot] = ns + ncap; }
+      start = ns;
+    }
+    if (gl == 0) { cell_base[slot] = start + cnt; tab[slot].cnt = word + nc; newcnt[slot] = 0u; }
+    __syncwarp(gmask);
+  }
+}
+
+// New frame, pass 3: the points go to the tails of their buckets and into the sequence ring.
+__global__ void __launch_bounds__(256) k_hash_add_scatter(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  const WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashIncr) return;
+  const unsigned* cell_base = d.cell_base + (size_t)lane_b * d.p.Hcap;
+  float4* sorted = d.sorted + (size_t)lane_b * d.p.Pcap;
+  float4* lin = d.lin + (size_t)lane_b * d.p.LinCap;
+  const unsigned lmask = (unsigned)d.p.LinCap - 1u;
+  const float4* slab = d.win + ((size_t)lane_b * d.p.slots + ws.nw_slab) * d.p.Ecap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ws.nw_cnt; i += gridDim.x * blockDim.x) {
+    float4 pt = slab[i];
+    const unsigned g = ws.nw_g + (unsigned)i;
+    lin[g & lmask] = pt;
+    const unsigned ps = d.pt_slot[(size_t)lane_b * d.p.Mcap + i];
+    if (ps == 0xffffffffu) continue;
+    pt.w = __uint_as_float(g);
+    sorted[cell_base[ps] + d.pt_rank[(size_t)lane_b * d.p.Mcap + i]] = pt;
+  }
+}
+
+// ---- full, ordered: one CTA per lane, frames scattered oldest first so that every bucket is in frame order ----
+constexpr int kFullThreads = 1024;
+__global__ void __launch_bounds__(kFullThreads) k_hash_full_ordered(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.x;
+  WinState& ws = d.wstate[lane_b];
+  if (ws.hmode != kHashFullOrdered) return;
+  hash_check_generation(ws);
+  const int tid = threadIdx.x;
+  const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+  const unsigned mask = (unsigned)d.p.Hcap - 1u, cmask = (1u << kCntBits) - 1u;
+  HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
+  unsigned* cap_end = d.cap_end + (size_t)lane_b * d.p.Hcap;
+  unsigned* pt_slot = d.pt_slot + (size_t)lane_b * d.p.Mcap;
+  unsigned* owners = d.owner_list + (size_t)lane_b * d.p.Mcap;
+  float4* sorted = d.sorted + (size_t)lane_b * d.p.Pcap;
+  float4* lin = d.lin + (size_t)lane_b * d.p.LinCap;
+  uint4* bw = reinterpret_cast<uint4*>(d.bloom + (size_t)lane_b * d.p.Bwords);
+  for (int i = tid; i < d.p.Bwords / 4; i += kFullThreads) bw[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  WinView v;
+  load_win_view(d, lane_b, &v, false);
+  const int total = v.total;
+  // pass 1: cells and their populations
+  for (int i = tid; i < total; i += kFullThreads) {
+    const float4 pt = win_point(d, lane_b, v, i);
+    if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { pt_slot[i] = 0xffffffffu; continue; }
+    bool created;
+    const unsigned slot = hash_find_or_create(tab, mask, gen, pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen), &created);
+    if (created) { owners[atomicAdd(&ws.n_owners, 1)] = slot; bloom_publish(d, lane_b, pt); }
+    atomicMax(&tab[slot].cnt, gen << kCntBits);
+    atomicAdd(&tab[slot].cnt, 1u);
+    pt_slot[i] = slot;
+  }
+  __syncthreads();
+  // pass 2: a region per cell with room for a few scans of growth; counts restart for the ordered scatter
+  const int ncell = ws.n_owners;
+  for (int j = tid; j < ncell; j += kFullThreads) {
+    const unsigned slot = owners[j], cnt = tab[slot].cnt & cmask, cap = 2u * cnt + 4u;   // first move after ~a window length of scans
+    const unsigned start = (unsigned)atomicAdd(&ws.bump, (int)cap);
+    tab[slot].start = start; cap_end[slot] = start + cap; tab[slot].cnt = gen << kCntBits;
+  }
+  if (tid == 0) ws.cells_used = ncell;
+  __syncthreads();
+  // pass 3: frame after frame (sequence number = logical index, hash_begin renumbered the frames)
+  for (int f = 0; f < v.nframes; ++f) {
+    const int lo = v.prefix[f], hi = v.prefix[f + 1];
+    for (int i = lo + tid; i < hi; i += kFullThreads) {
+      float4 pt = win_point(d, lane_b, v, i);
+      lin[i] = pt;
+      const unsigned slot = pt_slot[i];
+      if (slot == 0xffffffffu) continue;
+      const unsigned rank = atomicAdd(&tab[slot].cnt, 1u) & cmask;
+      pt.w = __int_as_float(i);
+      sorted[tab[slot].start + rank] = pt;
+    }
+    __syncthreads();
+  }
+}
+
 int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   const int lane0 = lr.lane0, nlanes = lr.nlanes;
-  int blocks = (d.p.Mcap + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  const dim3 g(blocks, nlanes);
-  const int nf = launch_window_filter(d, s, lr);
-  k_bloom_clear<<<dim3(std::max(1, std::min(d.p.Bwords / 4 / 256, 64)), nlanes), 256, 0, s>>>(d, lane0);
-  k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
-  k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
-  k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
-  return 4 + nf;
+  if (d.p.mapping || d.p.filter_local_map) {   // the target is replaced wholesale every scan: full, fast
+    int blocks = (d.p.Mcap + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const dim3 g(blocks, nlanes);
+    const int nf = launch_window_filter(d, s, lr);
+    k_bloom_clear<<<dim3(std::max(1, std::min(d.p.Bwords / 4 / 256, 64)), nlanes), 256, 0, s>>>(d, lane0);
+    k_hash_insert<<<g, 256, 0, s>>>(d, lane0);
+    k_hash_alloc<<<g, 256, 0, s>>>(d, lane0);
+    k_hash_scatter<<<g, 256, 0, s>>>(d, lane0);
+    return 4 + nf;
+  }
+  const dim3 ge((d.p.Ecap + 255) / 256, nlanes);
+  k_hash_full_ordered<<<nlanes, kFullThreads, 0, s>>>(d, lane0);
+  k_hash_evict<<<ge, 256, 0, s>>>(d, lane0);
+  k_hash_add_count<<<ge, 256, 0, s>>>(d, lane0);
+  k_hash_grow<<<dim3((d.p.Ecap * kGrowGroup / 4 + 255) / 256, nlanes), 256, 0, s>>>(d, lane0);   // ~4 groups' worth of threads per possible cell pair; grid-stride
+  k_hash_add_scatter<<<ge, 256, 0, s>>>(d, lane0);
+  return 5;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -564,10 +805,11 @@ __device__ __forceinline__ bool line_gate(const DevBuffers& d, int lane_b, int e
   float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
   if (nn_idx[0] >= 0) {  // five neighbours with d2 < 1.0 (src/laser_odometry.cc:324)
     gt |= 1;
-    const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
+    const float4* lin = d.lin + (size_t)lane_b * p.LinCap;   // ring by sequence number
+    const unsigned lmask = (unsigned)p.LinCap - 1u;
     float4 nn[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) nn[r] = lin[nn_idx[r]];
+    for (int r = 0; r < 5; ++r) nn[r] = lin[(unsigned)nn_idx[r] & lmask];
     // centroid and scatter in double, neighbour order (src/laser_odometry.cc:325-340)
     double mx = 0.0, my = 0.0, mz = 0.0;
 #pragma unroll
@@ -641,7 +883,7 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
     const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
     const unsigned hmask = (unsigned)p.Hcap - 1u, bmask = (unsigned)p.Bwords - 1u;
     const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
-    const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
+    const float4* sorted = d.sorted + (size_t)lane_b * p.Pcap;
     const unsigned* bloom = d.bloom + (size_t)lane_b * p.Bwords;
     Knn5 k;
 #pragma unroll
@@ -725,7 +967,7 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
       if (d.gate) {
         const size_t o = (size_t)lane_b * p.Ecap + e;
         for (int r = 0; r < 5; ++r) {
-          d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+          d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)((unsigned)k.k[r] - win_g0(d, lane_b));   // logical index
           d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
         }
         d.q_world[o] = make_float4(qx, qy, qz, c.w);
@@ -816,7 +1058,7 @@ __global__ void __launch_bounds__(kCtaQ, 8) k_associate_cta(DevBuffers d, int la
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned hmask = (unsigned)p.Hcap - 1u, bmask = (unsigned)p.Bwords - 1u;
   const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
-  const float4* sorted = d.sorted + (size_t)lane_b * p.Mcap;
+  const float4* sorted = d.sorted + (size_t)lane_b * p.Pcap;
   const unsigned* bloom = d.bloom + (size_t)lane_b * p.Bwords;
   // knn_out still holds this frame's first-iteration neighbours (k_predict starts every frame at outer_it 0)
   const bool seed_from_prev = outer_it == 1 && !force && shard_world == 1;
@@ -844,11 +1086,12 @@ __global__ void __launch_bounds__(kCtaQ, 8) k_associate_cta(DevBuffers d, int la
       if (seed_from_prev) {
         const int* prev = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
         if (prev[0] >= 0) {
-          const float4* lin = d.lin + (size_t)lane_b * p.Mcap;
+          const float4* lin = d.lin + (size_t)lane_b * p.LinCap;
+          const unsigned lmask = (unsigned)p.LinCap - 1u;
           float m = 0.0f;
 #pragma unroll
           for (int r = 0; r < 5; ++r) {
-            const float4 pt = lin[prev[r]];
+            const float4 pt = lin[(unsigned)prev[r] & lmask];
             const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
             m = fmaxf(m, __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
           }
@@ -929,7 +1172,7 @@ __global__ void __launch_bounds__(kCtaQ, 8) k_associate_cta(DevBuffers d, int la
     if (d.gate) {
       const size_t o = (size_t)lane_b * p.Ecap + e;
       for (int r = 0; r < 5; ++r) {
-        d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+        d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)((unsigned)k.k[r] - win_g0(d, lane_b));   // logical index
         d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
       }
       d.q_world[o] = make_float4(qx, qy, qz, d.edges[(size_t)lane_b * p.Ecap + e].w);
@@ -1059,7 +1302,7 @@ int launch_lmap_add(const DevBuffers& d, cudaStream_t s, int lane, const float4*
 }
 
 // rebuild the hash of one lane after the window / received map was edited from the host
-__global__ void k_hash_begin(DevBuffers d, int lane_b) { if (threadIdx.x == 0) hash_begin(d, lane_b); }
+__global__ void k_hash_begin(DevBuffers d, int lane_b) { if (threadIdx.x == 0) hash_begin(d, lane_b, true); }
 int launch_hash_rebuild(const DevBuffers& d, cudaStream_t s, int lane) {
   k_hash_begin<<<1, 32, 0, s>>>(d, lane);
   return 1 + launch_hash_build(d, s, LaneRange{lane, 1});

@@ -419,3 +419,33 @@ def test_hash_generation_wrap(cuda_lib):
             checked += 1
     assert checked == 11
     ctx.close()
+
+
+def test_incremental_hash_every_frame(cuda_lib):
+    """The voxel hash follows the window incrementally (evict the oldest frame from the heads of its buckets, append the
+    new frame at the tails; full rebuilds only when pool / table headroom runs out).  A drifting cloud over 400 frames:
+    cells empty out and come back, buckets move to larger regions, frames of different sizes (one empty, some with
+    non-finite points); the association is checked against the oracle on EVERY frame."""
+    rng = np.random.default_rng(33)
+    ctx = api.Context(prev_frames=6, max_points=2048, scan_lines=16)
+    frames = []
+    for f in range(400):
+        n = 0 if f == 17 else int(rng.integers(20, 300))
+        centre = np.array([0.02 * f, 0.5 * np.sin(0.05 * f), 0.0, 0.0])
+        w = (rng.normal(size=(n, 4)) * [1.2, 1.2, 0.4, 1.0] + centre).astype(np.float32)
+        if f % 23 == 5 and n > 3:
+            w[1, 0] = np.nan
+            w[2, 2] = np.inf
+        ctx.lmap_add(w)
+        frames = (frames + [w])[-6:]
+        window = np.concatenate(frames)
+        q = (rng.normal(size=(150, 4)) * [1.0, 1.0, 0.4, 1.0] + centre).astype(np.float32)
+        o = oracle.associate(q, np.eye(4), window)
+        g = ctx.associate(q, np.eye(4))
+        assert g["n_map"] == len(window), f
+        ok = o["tie"] == 0
+        assert np.array_equal(g["gate"][ok], o["gate"][ok]), f
+        sel = ok & ((o["gate"] & 1) == 1)
+        assert np.array_equal(g["knn_idx"][sel], o["knn_idx"][sel]), f
+        assert np.array_equal(g["knn_d2"][sel].view(np.uint32), o["knn_d2"][sel].view(np.uint32)), f
+    ctx.close()
