@@ -650,6 +650,13 @@ def point_sharded_run(api, torch, dist, rank, world, local, nframes, warm, senso
         single_ms = e0.elapsed_time(e1) / (nframes - warm)
         d = ctx.scan_diag(0)
         out.update({"edges_per_scan": int(np.mean(ne)), "map_points": int(d.n_map[0]), "single_gpu_ms_per_scan": round(single_ms, 4)})
+        # per-stage device times of one more scan (events between the stages; outside the timed span)
+        ctx.stage_timing(True)
+        ctx.scan_batch_ptrs([dscans[nframes - 1].data_ptr()], [len(scans[nframes - 1])], 16, on_device=True)
+        ctx.sync()
+        sms, _ = ctx.stage_times()
+        ctx.stage_timing(False)
+        out["single_gpu_stage_ms"] = {k: round(float(v), 4) for k, v in zip(api.STAGE_NAMES, sms)}
         ctx.close()
     if world > 1:
         uid = [api.shard_unique_id() if rank == 0 else None]
@@ -659,6 +666,12 @@ def point_sharded_run(api, torch, dist, rank, world, local, nframes, warm, senso
         l0 = ctx.launch_count
         ms, poses, ne = run(ctx, warm)
         launches = ctx.launch_count - l0
+        ctx.stage_timing(True)   # one more scan with events between the stages (every rank: the collectives need all of them)
+        ctx.scan_batch_ptrs([dscans[nframes - 1].data_ptr()], [len(scans[nframes - 1])], 16, on_device=True)
+        ctx.sync()
+        sms, _ = ctx.stage_times()
+        ctx.stage_timing(False)
+        out["sharded_stage_ms"] = {k: round(float(v), 4) for k, v in zip(api.STAGE_NAMES, sms)}
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # every rank must hold bitwise the same poses (the LM controller is replicated)

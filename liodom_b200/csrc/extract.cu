@@ -397,7 +397,11 @@ __device__ int run_region_reg(const RingView& rv, int lo, int hi, int epr, int* 
   return np;
 }
 
-__global__ void __launch_bounds__(256) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
+// NT: threads per CTA.  256 for rings that fit shared memory (4 CTAs per SM); 1024 when the expected ring is longer
+// than the shared-memory capacity (1M-point scans: 15,625 points per ring, one CTA per ring is all the parallelism
+// there is, so the CTA should be as wide as possible: 32 warps for the curvature and the 64 regions).
+template <int NT>
+__global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y, ring = ring0 + blockIdx.x;   // ring0 > 0: ring-sharded extraction
   const int L = p.scan_lines, R = p.scan_regions, epr = p.edges_per_region, E1 = epr + 1;
@@ -607,6 +611,9 @@ int extract_ring_cap(const DevParams& p) {
   return (int)cap;
 }
 
+// the expected ring (max_points / scan_lines + 5 %) does not fit the shared-memory ring buffer: global-memory path
+static bool extract_long_rings(const DevParams& p, int ring_cap) { return ((long)p.Ncap * 21 / 20) / p.scan_lines > ring_cap; }
+
 int launch_split(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   const dim3 g(d.p.chunks, lr.nlanes);
   k_split_count<<<g, 256, 0, s>>>(d, lr.lane0);
@@ -632,7 +639,9 @@ static cudaError_t raise_dynamic_smem_limit(K kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
 }
 cudaError_t configure_extract_kernels() {
-  cudaError_t e = raise_dynamic_smem_limit(k_extract);
+  cudaError_t e = raise_dynamic_smem_limit(k_extract<256>);
+  if (e != cudaSuccess) return e;
+  e = raise_dynamic_smem_limit(k_extract<1024>);
   if (e != cudaSuccess) return e;
   return raise_dynamic_smem_limit(k_compact);
 }
@@ -644,7 +653,8 @@ size_t extract_smem_needed(const DevParams& p) {   // + 4 KB for the kernels' st
 int launch_extract_rings(const DevBuffers& d, cudaStream_t s, LaneRange lr, int ring0, int nrings) {
   const int ring_cap = extract_ring_cap(d.p);
   const size_t sm = extract_smem_bytes(d.p, ring_cap);
-  k_extract<<<dim3(nrings, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, 0, ring0);
+  if (extract_long_rings(d.p, ring_cap)) k_extract<1024><<<dim3(nrings, lr.nlanes), 1024, sm, s>>>(d, lr.lane0, ring_cap, 0, ring0);
+  else k_extract<256><<<dim3(nrings, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, 0, ring0);
   return 1;
 }
 int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
@@ -656,7 +666,8 @@ int launch_compact(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
 int launch_extract(const DevBuffers& d, cudaStream_t s, LaneRange lr, bool want_keys) {
   const int ring_cap = extract_ring_cap(d.p);
   const size_t sm = extract_smem_bytes(d.p, ring_cap);
-  k_extract<<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0, 0);
+  if (extract_long_rings(d.p, ring_cap)) k_extract<1024><<<dim3(d.p.scan_lines, lr.nlanes), 1024, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0, 0);
+  else k_extract<256><<<dim3(d.p.scan_lines, lr.nlanes), 256, sm, s>>>(d, lr.lane0, ring_cap, want_keys ? 1 : 0, 0);
   const int LR = d.p.scan_lines * d.p.scan_regions;
   k_compact<<<lr.nlanes, 1024, (LR + 32) * sizeof(int), s>>>(d, lr.lane0);
   return 2;

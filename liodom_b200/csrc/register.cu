@@ -1219,7 +1219,10 @@ static int assoc_group_size(long long edges_in_flight) {
 
 static void launch_associate_any(const DevBuffers& d, cudaStream_t s, int lane0, int nlanes, int edges_per_lane, int outer_it, int force,
                                  const double* pose_override, int rank, int world) {
-  const int G = assoc_group_size((long long)edges_per_lane * nlanes);
+  int G = assoc_group_size((long long)edges_per_lane * nlanes);
+  // Edge-sharded mode: a rank's share is one partial wave, so the stage lasts as long as the longest per-edge chain;
+  // spend the idle threads on shorter chains (the thresholds above were measured on whole C1 batches).
+  if (world > 1 && !getenv("LIODOM_ASSOC_GROUP")) G = edges_per_lane <= 16384 ? 16 : (edges_per_lane <= 32768 ? 8 : 4);
   const dim3 g((unsigned)(((long long)edges_per_lane * G + kAssocThreads - 1) / kAssocThreads), nlanes);
   if (G == 16) k_associate<16><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
   else if (G == 8) k_associate<8><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);

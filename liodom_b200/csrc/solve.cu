@@ -371,25 +371,52 @@ static void launch_solve_kernel(const DevBuffers& d, cudaStream_t s, int lane0, 
 }
 
 // ---- point-sharded solve: evaluation over this rank's edges, all-reduce, replicated controller ----
-constexpr int kShardEvalThreads = 1024;
+// One kernel per LM evaluation, kShardCtas CTAs: every CTA's thread 0 first advances the trust-region controller from
+// the all-reduced sums of the previous evaluation (redundantly and identically: the state is double-buffered, CTA 0
+// publishes the new copy), then the CTAs evaluate this rank's share of the residual blocks at the controller's next
+// point; partial sums go to global memory and the last CTA to arrive adds them in CTA order (deterministic) into
+// the buffer the all-reduce works on.  Per solve: 6 launches + 5 ncclAllReduce(29 x f64).
+constexpr int kShardThreads = 256;
+constexpr int kShardCtas = 16;
 constexpr int kShardMaxEvals = 5;   // the initial evaluation + one (cost + Jacobian) evaluation per iteration (<= 4)
 
-size_t shard_ctrl_bytes() { return sizeof(LmCtrl); }
+struct ShardState {
+  LmCtrl c[2];
+  double partial[kShardCtas][32];
+  unsigned ticket;
+};
 
-__global__ void k_shard_begin(DevBuffers d, int lane_b) {
-  if (threadIdx.x != 0) return;
-  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
-  const OdomState& os = d.ostate[lane_b];
-  lm_init(c, os);
-  if (!os.init) c.action = 2;   // first frame: no solve
-}
+size_t shard_ctrl_bytes() { return sizeof(ShardState); }
 
-__global__ void __launch_bounds__(kShardEvalThreads) k_shard_eval(DevBuffers d, int lane_b, int rank, int world) {
+__global__ void __launch_bounds__(kShardThreads) k_shard_step(DevBuffers d, int lane_b, int rank, int world, int e, int outer_it) {
   const DevParams& p = d.p;
-  const LmCtrl& c = static_cast<const LmCtrl*>(d.shard_ctrl)[lane_b];
+  ShardState& st = static_cast<ShardState*>(d.shard_ctrl)[lane_b];
   const OdomState& os = d.ostate[lane_b];
-  __shared__ double sred[(kShardEvalThreads / 32) * kNumAcc];
+  __shared__ LmCtrl c;
+  __shared__ double sred[(kShardThreads / 32) * kNumAcc];
   __shared__ double total[kNumAcc];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    if (e == 0) {
+      lm_init(c, os);
+      if (!os.init) c.action = 2;   // first frame: no solve
+    } else {
+      c = st.c[e & 1];
+      const double* acc = d.shard_acc + (size_t)lane_b * 32;
+      if (c.action == 0) lm_after_jacobian(c, acc);
+      else if (c.action == 1) lm_after_cost(c, acc);
+    }
+    if (blockIdx.x == 0) st.c[(e + 1) & 1] = c;
+  }
+  __syncthreads();
+  if (e == kShardMaxEvals) {   // the controller has seen every evaluation: commit
+    if (blockIdx.x == 0 && tid == 0 && os.init) {
+      solve_commit(d, lane_b, outer_it, c);
+      d.diag[lane_b].n_matches[outer_it] = c.sum.num_residual_blocks;   // all ranks' matches (from the reduced count)
+    }
+    return;
+  }
   const int action = c.action;
   double acc[kNumAcc];
 #pragma unroll
@@ -403,7 +430,7 @@ __global__ void __launch_bounds__(kShardEvalThreads) k_shard_eval(DevBuffers d, 
     const float* blocks = d.blocks + (size_t)lane_b * p.Ecap * 10;
     const int* perm = d.perm + (size_t)lane_b * p.Ecap;
     const double min_d = p.min_range, inv_range = 1.0 / (p.max_range - p.min_range);
-    for (int t = rank * share + threadIdx.x; t < t1; t += blockDim.x) {
+    for (int t = rank * share + blockIdx.x * kShardThreads + tid; t < t1; t += gridDim.x * kShardThreads) {
       const float* b = blocks + (size_t)perm[t] * 10;
       if (b[9] == 0.0f) continue;
       double cab[9];
@@ -413,35 +440,31 @@ __global__ void __launch_bounds__(kShardEvalThreads) k_shard_eval(DevBuffers d, 
     }
   }
   block_reduce<0, kNumAcc>(acc, sred, total);
-  if (threadIdx.x < kNumAcc) d.shard_acc[(size_t)lane_b * 32 + threadIdx.x] = total[threadIdx.x];
-}
-
-__global__ void k_shard_ctrl(DevBuffers d, int lane_b) {
-  if (threadIdx.x != 0) return;
-  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
-  const double* acc = d.shard_acc + (size_t)lane_b * 32;
-  if (c.action == 0) lm_after_jacobian(c, acc);
-  else if (c.action == 1) lm_after_cost(c, acc);
-}
-
-__global__ void k_shard_finish(DevBuffers d, int lane_b, int outer_it) {
-  if (threadIdx.x != 0) return;
-  LmCtrl& c = static_cast<LmCtrl*>(d.shard_ctrl)[lane_b];
-  if (!d.ostate[lane_b].init) return;
-  solve_commit(d, lane_b, outer_it, c);
-  d.diag[lane_b].n_matches[outer_it] = c.sum.num_residual_blocks;   // all ranks' matches (from the reduced count)
+  if (tid < kNumAcc) st.partial[blockIdx.x][tid] = total[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {   // every CTA's partials are visible: add them in CTA order
+    __threadfence();
+    if (tid < kNumAcc) {
+      double sum = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) sum += ((volatile double*)st.partial[b])[tid];
+      d.shard_acc[(size_t)lane_b * 32 + tid] = sum;
+    }
+    if (tid == 0) st.ticket = 0u;
+  }
 }
 
 int launch_solve_shard(const DevBuffers& d, cudaStream_t s, int lane, int outer_it, const ShardComm* sc, int* nccl_rc) {
   int k = 0;
-  k_shard_begin<<<1, 32, 0, s>>>(d, lane); ++k;
-  for (int e = 0; e < kShardMaxEvals; ++e) {
-    k_shard_eval<<<1, kShardEvalThreads, 0, s>>>(d, lane, sc->rank, sc->world); ++k;
-    const int rc = shard_allreduce_f64(sc, d.shard_acc + (size_t)lane * 32, kNumAcc, s);
-    if (rc != 0 && nccl_rc) *nccl_rc = rc;
-    k_shard_ctrl<<<1, 32, 0, s>>>(d, lane); ++k;
+  for (int e = 0; e <= kShardMaxEvals; ++e) {
+    k_shard_step<<<kShardCtas, kShardThreads, 0, s>>>(d, lane, sc->rank, sc->world, e, outer_it); ++k;
+    if (e < kShardMaxEvals) {
+      const int rc = shard_allreduce_f64(sc, d.shard_acc + (size_t)lane * 32, kNumAcc, s);
+      if (rc != 0 && nccl_rc) *nccl_rc = rc;
+    }
   }
-  k_shard_finish<<<1, 32, 0, s>>>(d, lane, outer_it); ++k;
   return k;
 }
 
