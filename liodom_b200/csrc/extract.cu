@@ -352,11 +352,39 @@ __device__ int run_region(const RingView& rv, int lo, int hi, int epr, int* pick
   return np;
 }
 
-// Register-cached variant for regions of at most 256 items (8 per lane): keys and availability
-// live in registers, the only shared-memory traffic in the loop is the gap tests around the pick.
+// Five consecutive bits of the gap bitmap starting at ring index p (bit k = "points p+k and p+k+1 are more than
+// sqrt(0.05) m apart", src/feature_extractor.cc:281-291): bit 0 is index p.
+__device__ __forceinline__ unsigned gap5(const unsigned* gapbits, int p, int wcap) {
+  const int w0 = p >> 5;
+  const unsigned a = gapbits[w0], b = w0 + 1 < wcap ? gapbits[w0 + 1] : 0u;
+  return __funnelshift_r(a, b, p & 31) & 0x1fu;
+}
+
+// Forward suppression of a region's picks beyond its end `hi`, from the gap bitmap (see region_spill).
+__device__ __forceinline__ unsigned region_spill_fast(const unsigned* gapbits, int wcap, const int* picks, int np, int hi, int n, int ln) {
+  unsigned m = 0;
+  for (int k = ln; k < np; k += 32) {
+    const int idx = picks[k];
+    if (idx + 5 >= hi && hi + 4 < n) {
+      const unsigned f = gap5(gapbits, idx, wcap);
+      const int nf = f ? (__ffs(f) - 1) : 5;
+      for (int l = 1; l <= nf; ++l)
+        if (idx + l >= hi) m |= 1u << (idx + l - hi);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  return m;
+}
+
+// Register-cached variant for regions of at most 256 items (8 per lane): keys and availability live in registers.
+// The +-5 suppression reads the precomputed gap bitmap (one bit per consecutive pair of ring points, filled once per
+// ring with every lane busy) instead of evaluating ten FP64 gaps per pick in ten lanes; the warp arg-max is three
+// redux operations on the order-preserving integer image of the non-negative key (high word, low word among ties,
+// lowest index among ties) instead of five 96-bit shuffle rounds.
 // `premask`: bit b set <=> ring index lo + b is already suppressed by the previous region's picks.
 // Same selection as run_region (total order smoothness desc, index asc).
-__device__ int run_region_reg(const RingView& rv, int lo, int hi, int epr, int* picks, int ln, unsigned premask) {
+__device__ int run_region_reg(const RingView& rv, const unsigned* gapbits, int wcap, int lo, int hi, int epr, int* picks, int ln, unsigned premask) {
   double kk[8];
   unsigned dead = 0;
 #pragma unroll
@@ -371,28 +399,24 @@ __device__ int run_region_reg(const RingView& rv, int lo, int hi, int epr, int* 
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (!((dead >> j) & 1u) && kk[j] > bk) { bk = kk[j]; bi = lo + ln + 32 * j; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-    }
+    // keys are sums of squares (>= +0): their bit patterns order like the values; a lane without a live item offers 0
+    const unsigned long long kb = bi == 0x7fffffff ? 0ull : (unsigned long long)__double_as_longlong(bk);
+    const unsigned khi = (unsigned)(kb >> 32), klo = (unsigned)kb;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, khi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, khi == mh ? klo : 0u);
+    bi = (int)__reduce_min_sync(0xffffffffu, (khi == mh && klo == ml) ? (unsigned)bi : 0x7fffffffu);
+    bk = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
     if (bi == 0x7fffffff) break;            // every item already picked
     if (bk < 0.1 || np > epr) break;        // src/feature_extractor.cc:270
     if (ln == 0) picks[np] = bi;
     ++np;
-    // +-5 suppression, gap-limited (src/feature_extractor.cc:280-310): lanes 0-4 forward, 8-12 backward
-    bool brk = false;
-    if (ln < 5) { const int l = ln + 1; brk = gap2(rv.P[bi + l], rv.P[bi + l - 1]) > 0.05; }
-    else if (ln >= 8 && ln < 13) { const int l = ln - 7; brk = gap2(rv.P[bi - l], rv.P[bi - l + 1]) > 0.05; }
-    const unsigned bm = __ballot_sync(0xffffffffu, brk);
-    const unsigned f = bm & 0x1fu, b = (bm >> 8) & 0x1fu;
-    const int nf = f ? (__ffs(f) - 1) : 5, nb = b ? (__ffs(b) - 1) : 5;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = lo + ln + 32 * j;
-      if (i >= bi - nb && i <= bi + nf) dead |= 1u << j;
-    }
+    // +-5 suppression, gap-limited (src/feature_extractor.cc:280-310)
+    const unsigned f = gap5(gapbits, bi, wcap), bb = gap5(gapbits, bi - 5, wcap);
+    const int nf = f ? (__ffs(f) - 1) : 5;                // forward: stop before the first wide gap
+    const int nb = bb ? (__clz(bb) - 27) : 5;             // backward: bit 4 is the pair (bi-1, bi); highest set bit h -> 4 - h
+    const int first = bi - nb;
+    const int i = first + ((ln - (first - lo)) & 31);     // this lane's only index in [first, first + 32)
+    if (i <= bi + nf && i >= lo && i < hi) dead |= 1u << ((i - lo) >> 5);
   }
   return np;
 }
@@ -442,7 +466,7 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(smem_u32(sp)), "l"(gp), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
     }
-    for (int k = tid; k < 2 * wcap; k += blockDim.x) sbits[k] = 0u;  // overlap with the copy
+    for (int k = tid; k < wcap; k += blockDim.x) sbits[k] = 0u;  // overlap with the copy (the gap bitmap behind it is written whole)
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -478,6 +502,16 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
     sk[j] = key;
     if (gkeys && in_smem) gkeys[j] = key;
   }
+  if (in_smem) {
+    // gap bitmap: bit j <=> consecutive ring points j, j+1 are more than sqrt(0.05) m apart (the +-5 suppression's
+    // break test, src/feature_extractor.cc:281-291 / :297-307: the same squared gap in both directions)
+    for (int base = tid & ~31; base < n; base += blockDim.x) {
+      const int j = base + ln;
+      const bool g = j + 1 < n && gap2(rv.P[j + 1], rv.P[j]) > 0.05;
+      const unsigned word = __ballot_sync(0xffffffffu, g);
+      if (ln == 0) stbits[base >> 5] = word;
+    }
+  }
   __syncthreads();
 
   const int total = n - 10, sector = total / R;
@@ -488,10 +522,10 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
   // speculative pass: every region on its own (no premask), marks confined to the region
   for (int r = w; r < R; r += nw) {
     const int lo = sector * r + 5, hi = (r == R - 1 ? total : sector * (r + 1)) + 5;
-    const int np = fast ? run_region_reg(rv, lo, hi, epr, picks + r * E1, ln, 0u) : run_region(rv, lo, hi, epr, picks + r * E1, ln);
+    const int np = fast ? run_region_reg(rv, stbits, wcap, lo, hi, epr, picks + r * E1, ln, 0u) : run_region(rv, lo, hi, epr, picks + r * E1, ln);
     if (ln == 0) npicks[r] = np;
     __syncwarp();
-    const unsigned sp = region_spill(rv, picks + r * E1, np, hi, ln);
+    const unsigned sp = fast ? region_spill_fast(stbits, wcap, picks + r * E1, np, hi, n, ln) : region_spill(rv, picks + r * E1, np, hi, ln);
     if (ln == 0) s_spill[r] = sp;
   }
   __syncthreads();
@@ -514,7 +548,7 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
         rerun = __any_sync(0xffffffffu, clash);
       }
       if (rerun) {
-        if (fast) np = run_region_reg(rv, lo, hi, epr, picks + r * E1, ln, spill_prev);
+        if (fast) np = run_region_reg(rv, stbits, wcap, lo, hi, epr, picks + r * E1, ln, spill_prev);
         else {
           // rerun with the true premask: clear the region's bits, set the spilled ones
           for (int i = (lo >> 5) + ln; i <= ((hi - 1) >> 5); i += 32) {
@@ -531,7 +565,7 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
         if (ln == 0) npicks[r] = np;
         __syncwarp();
       }
-      const unsigned spill_out = rerun ? region_spill(rv, picks + r * E1, np, hi, ln) : s_spill[r];
+      const unsigned spill_out = !rerun ? s_spill[r] : (fast ? region_spill_fast(stbits, wcap, picks + r * E1, np, hi, n, ln) : region_spill(rv, picks + r * E1, np, hi, ln));
       carry = ((hi - lo) >= 32 ? 0u : (carry >> (hi - lo))) | spill_out;
     }
   }
