@@ -8,10 +8,11 @@
 TAG=${1:-r02}
 LANES=${2:-128}
 export LIODOM_LANE_GROUPS=1
-PRE=$(( (16 + 3) * 18 ))     # pre-roll 16 + warm-up 3 steps, 18 launches per step with one lane group
-BENCH="python bench.py --lanes $LANES --steps 2 --warmup 3 --no-cpu-baseline --no-stage-pass --no-single-stream"
+PER=19                       # launches per step with one lane group (incremental hash: 5 build kernels)
+PRE=$(( (16 + 3) * PER ))    # pre-roll 16 + warm-up 3 steps
+BENCH="python bench.py --lanes $LANES --steps 2 --warmup 3 --no-cpu-baseline --no-stage-pass --no-single-stream --no-sharded-block --no-xyz12"
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s $PRE -c 36 --csv --log-file gpurun_out/launches_${TAG}_lanes${LANES}.csv $BENCH > gpurun_out/prof_${TAG}_a.log 2>&1
-ncu --set full --clock-control none -s $PRE -c 18 -o gpurun_out/step_${TAG}_lanes${LANES} -f $BENCH > gpurun_out/prof_${TAG}_b.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s $PRE -c $(( 2 * PER )) --csv --log-file gpurun_out/launches_${TAG}_lanes${LANES}.csv $BENCH > gpurun_out/prof_${TAG}_a.log 2>&1
+ncu --set full --clock-control none -s $PRE -c $PER -o gpurun_out/step_${TAG}_lanes${LANES} -f $BENCH > gpurun_out/prof_${TAG}_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_associate -s $(( (16 + 3) * 2 )) -c 2 -o gpurun_out/k_associate_${TAG}_lanes${LANES} -f $BENCH > gpurun_out/prof_${TAG}_c.log 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches_${TAG}_lanes${LANES}.csv
