@@ -95,3 +95,32 @@ def test_batch128_cta_level_association(cuda_lib, monkeypatch):
     monkeypatch.setenv("LIODOM_ASSOC_CTA", "1")
     w = _run_batch(128, "device")
     print("batch 128, CTA-level association: worst pose error %.3g m %.3g rad" % (w[0], w[1]))
+
+
+@pytest.mark.parametrize("name", ["c2_ouster", "c3_stress"])
+def test_batch_other_baseline_shapes(cuda_lib, name):
+    """The other BASELINE.json shapes through the batched path with a full window (the incremental voxel hash with
+    21-frame / 128-ring windows): C2 = OS1-128 organised clouds, C3 = scan_regions / edges_per_region doubled and
+    prev_frames = 20.  8 lanes (4 seeds), every lane and frame against the oracle's free run."""
+    from liodom_b200 import synth
+    if name == "c2_ouster":
+        sensor, nfr = "os1_128", 18
+        w, h = synth.sensor_shape(sensor)
+        kw = dict(lidar_type=1, scan_lines=128, prev_frames=15)
+        maxp = 262144
+    else:
+        sensor, nfr, w, h = "hdl64", 24, 0, 0
+        kw = dict(scan_regions=16, edges_per_region=20, prev_frames=20)
+        maxp = 131072
+    seeds = [1000, 1001, 1002, 1003]
+    seqs = [get_sequence(sensor, sd, nfr)[0] for sd in seeds]
+    op = oracle.make_params(**kw)
+    oruns = [oracle.run_sequence(op, sq, w, h)[0] for sq in seqs]
+    ctx = api.Context(batch=8, max_points=maxp, **kw)
+    for f in range(nfr):
+        ctx.scan_batch([seqs[l % 4][f] for l in range(8)], width=w, height=h)
+        poses, ne = ctx.results()
+        for l in range(8):
+            dt, dr = pose_err(poses[l], oruns[l % 4][f])
+            assert dt < TOL_T and dr < TOL_R, "%s lane %d frame %d: %g m, %g rad" % (name, l, f, dt, dr)
+    ctx.close()
