@@ -13,6 +13,7 @@ namespace liodom {
 
 constexpr int kSolveThreads = 256;
 constexpr int kNumAcc = 29;  // 21 (upper H) + 6 (g) + cost + block count
+constexpr int kValidCap = 8192;  // valid residual blocks a CTA can list in shared memory (beyond: the uncompacted loop)
 
 struct LmCtrl {
   double x[7], xc[7];
@@ -288,6 +289,33 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_solve(DevBuffers d, int 
     lm_init(c, os);
     if (!F32) for (int k = 0; k < 7; ++k) c.x[k] = qt_inout[k];
   }
+  // Compact the residual blocks this CTA owns (a contiguous share of the edge list) into a list of the VALID ones:
+  // only ~half of the edges pass the line gate, and skipping them inside the evaluation loop left 18 of 32 threads
+  // busy per instruction (profiles/step_r02z_lanes128.txt).  Stable (edge order), so the sums stay deterministic.
+  __shared__ unsigned short vlist[kValidCap];
+  __shared__ int wcnt[kSolveThreads / 32 + 1];
+  __shared__ int nvalid_s;
+  const int per = (n + (int)C - 1) / (int)C;
+  const int share0 = (int)crank * per, share1 = min(n, share0 + per);
+  const bool compact = F32 && per <= kValidCap && n <= 65535;
+  if (compact) {
+    const int ln = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int base = 0;
+    for (int i0 = share0; i0 < share1; i0 += blockDim.x) {
+      const int i = i0 + (int)threadIdx.x;
+      const bool ok = i < share1 && blocks[(size_t)i * 10 + 9] != 0.0f;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ln == 0) wcnt[w] = __popc(m);
+      __syncthreads();
+      int off = base;
+      for (int ww = 0; ww < w; ++ww) off += wcnt[ww];
+      if (ok) vlist[off + __popc(m & ((1u << ln) - 1u))] = (unsigned short)i;
+      for (int ww = 0; ww < nw; ++ww) base += wcnt[ww];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) nvalid_s = base;
+    __syncthreads();
+  }
   const LmCtrl* lead = cluster.map_shared_rank(&c, 0);
   for (;;) {
     cluster.sync();   // the controller's decision is visible
@@ -304,6 +332,16 @@ __global__ void __launch_bounds__(kSolveThreads, OCC) k_solve(DevBuffers d, int 
     double acc[kNumAcc];
 #pragma unroll
     for (int k = 0; k < kNumAcc; ++k) acc[k] = 0.0;
+    if (compact) {
+      const int nv = nvalid_s;
+      for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+        const float* b = blocks + (size_t)vlist[j] * 10;
+        double cab[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cab[k] = (double)b[k];
+        eval_block<true>(cab, xs, min_d, inv_range, acc);   // cost and Jacobian in one pass (see lm_after_cost)
+      }
+    } else
     for (int i = (int)crank * blockDim.x + threadIdx.x; i < n; i += (int)C * blockDim.x) {
       double cab[9];
       if (F32) {
