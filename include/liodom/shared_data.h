@@ -4,6 +4,7 @@
 #ifndef INCLUDE_LIODOM_SHARED_DATA_H
 #define INCLUDE_LIODOM_SHARED_DATA_H
 
+#include <condition_variable>
 #include <mutex>
 #include <queue>
 
@@ -21,6 +22,12 @@ class SharedData {
   // extractor thread -> odometry thread: edge clouds by pointer, FIFO (:64-89)
   void pushFeatures(const PointCloud::Ptr& feat_in, Header& header);
   bool popFeatures(PointCloud::Ptr& feat_out, Header& header);
+  // Not in the reference: its workers sleep 2 ms after every loop turn (src/feature_extractor.cc:80,
+  // src/laser_odometry.cc:270), which caps a stream at < 500 scans/s and adds up to 4 ms of latency per scan.
+  // The workers here wait on the queue instead — at most `ms` milliseconds, returning at once when an item is
+  // there — so the same loop runs at the speed of the GPU stages.  Results are unaffected.
+  void waitPointCloud(int ms);
+  void waitFeatures(int ms);
   // mapping process -> odometry: latest local map, deep-copied both ways (:91-105)
   void setLocalMap(const PointCloud::Ptr& map_in);
   void getLocalMap(PointCloud::Ptr& map_out);
@@ -36,7 +43,7 @@ class SharedData {
   ~SharedData() {}
 
  private:
-  template <typename T> struct Fifo { std::mutex m; std::queue<T> items; std::queue<Header> headers; };
+  template <typename T> struct Fifo { std::mutex m; std::condition_variable cv; std::queue<T> items; std::queue<Header> headers; };
   static SharedData* instance_;
   static std::mutex instance_mutex_;
   Fifo<PointCloud::Ptr> scans_, feats_;

@@ -852,6 +852,21 @@ __constant__ unsigned char kNearOrder[27] = {
     0x1a, 0x26, 0x29,                         // two far + one near
     0x2a};                                    // three far
 
+// The same order on the CANONICAL occupancy word: occ_canonical reflects every axis whose near side is +1, so that
+// "near" is offset -1 for every lane and slot i of the order is one constant bit, bit = ((cz+1)*3 + (cy+1))*3 + (cx+1)
+// with c = 0 (own), -1 (near), +1 (far).  The slot test is then two instructions; the offsets are decoded only for
+// occupied slots (the per-slot decode was 10 % of k_associate<1>'s instructions).
+__constant__ unsigned kNearMask[27] = {
+    0x0002000, 0x0001000, 0x0000400, 0x0000010, 0x0000200, 0x0000008, 0x0000002, 0x0000001, 0x0004000,
+    0x0010000, 0x0400000, 0x0000800, 0x0008000, 0x0000020, 0x0000080, 0x0200000, 0x0080000, 0x0000004,
+    0x0000040, 0x0040000, 0x0020000, 0x0800000, 0x2000000, 0x0000100, 0x0100000, 0x1000000, 0x4000000};
+__device__ __forceinline__ unsigned occ_canonical(unsigned occ, int nx, int ny, int nz) {
+  if (nx > 0) occ = ((occ & 0x1249249u) << 2) | ((occ & 0x4924924u) >> 2) | (occ & 0x2492492u);
+  if (ny > 0) occ = ((occ & 0x01c0e07u) << 6) | ((occ & 0x70381c0u) >> 6) | (occ & 0x0e07038u);
+  if (nz > 0) occ = ((occ & 0x00001ffu) << 18) | ((occ & 0x7fc0000u) >> 18) | (occ & 0x003fe00u);
+  return occ;
+}
+
 // G threads per edge (G = 1 for large batches: least work; G = 4 when few edges are in flight:
 // shorter critical path): transform (A.1: double math, float store), exact 5-NN, line gate
 // (centroid, scatter, eigenvalues in FP64) and the residual block {c, a, b, valid}.
@@ -902,19 +917,19 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
         for (int r = 0; r < 9; ++r) occ |= bloom_row(bloom, bmask, cx - 1, 3, cy + r % 3 - 1, cz + r / 3 - 1) << (3 * r);
         const uint2 sc = hash_lookup(tab, hmask, gen, cx, cy, cz);
         knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, 3.0e38f, k);
-        occ &= ~(1u << 13);
         // neighbours nearest first (per axis: own, then the side of the nearer face, then the far side), so
         // that the bound tightens before the far cells are looked at and most of them fall to cell_min_d2
         const int nx = __fsub_rn(qx, kCell * (float)cx) < 0.5f * kCell ? -1 : 1;
         const int ny = __fsub_rn(qy, kCell * (float)cy) < 0.5f * kCell ? -1 : 1;
         const int nz = __fsub_rn(qz, kCell * (float)cz) < 0.5f * kCell ? -1 : 1;
+        occ = occ_canonical(occ & ~(1u << 13), nx, ny, nz);
         for (int i = 1; i < 27 && occ; ++i) {
+          const unsigned bit = kNearMask[i];
+          if (!(occ & bit)) continue;
+          occ &= ~bit;
           const unsigned code = kNearOrder[i];
           const int ax = code & 3, ay = (code >> 2) & 3, az = code >> 4;
           const int dx = ax == 0 ? 0 : (ax == 1 ? nx : -nx), dy = ay == 0 ? 0 : (ay == 1 ? ny : -ny), dz = az == 0 ? 0 : (az == 1 ? nz : -nz);
-          const unsigned bit = 1u << (((dz + 1) * 3 + (dy + 1)) * 3 + (dx + 1));
-          if (!(occ & bit)) continue;
-          occ &= ~bit;
           knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
         }
       }
@@ -976,6 +991,233 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
     if (G != 1) {
       const int nm = __popc(__ballot_sync(0xffffffffu, match));
       if (ln == 0 && nm) atomicAdd(&d.diag[lane_b].n_matches[outer_it], nm);
+    }
+  }
+  if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
+}
+
+// ---------------------------------------------------------------------------------------
+// Large batches: thread-per-edge search whose NEIGHBOUR-cell candidates are pooled over the warp.
+//
+// Replay of the C1 data (tools/assoc_work_analysis.py --warp-sim): a warp of the thread-per-edge kernel spends 62
+// four-candidate iterations per 32 edges, 12 on the own cells and 50 on neighbour cells, although the 32 edges together
+// hold only 16 iterations' worth of candidates: neighbouring edges differ widely in how many neighbour points survive
+// their bound.  So the search is split:
+//   phase A  (as before, one thread per edge) own cell, then the neighbour cells nearest first — scanned in place while
+//            the edge has fewer than five candidates (no bound yet), LISTED (start, count) in shared memory once it has
+//            a bound; cells the bound excludes are skipped as before;
+//   phase B  the warp's listed buckets form one candidate sequence that is cut into 32 equal chunks; every lane scans
+//            one chunk on behalf of the owning edges (query and bound read from shared memory) and pushes the candidates
+//            that pass the owner's bound (3 per edge on average) onto the owner's list in a per-warp pool;
+//   phase C  every owner merges its list into its five best.
+// The candidate set an edge sees is a superset of the one the thread-per-edge kernel examines under its progressively
+// tightened bound, every rejected candidate is beyond the bound the edge already holds, and the five best of a set do
+// not depend on the order of insertion: results are bit-identical.  When the pool runs over, owners that lost a
+// candidate scan their listed buckets themselves.
+// ---------------------------------------------------------------------------------------
+constexpr int kPoolSegs = 8;       // listed neighbour buckets per edge (further ones are scanned in place)
+constexpr int kPoolSurv = 224;     // pooled candidates per warp that passed their owner's bound
+constexpr unsigned kPoolNil = 0xffffu;
+
+struct PoolWarp {
+  uint2 seg[kPoolSegs][32];
+  float qx[32], qy[32], qz[32], ub[32];
+  unsigned pre[33];                       // exclusive prefix of the listed candidates per owner lane
+  unsigned head[32];                      // owner's list of pooled candidates
+  unsigned long long surv[kPoolSurv];
+  unsigned short next[kPoolSurv];
+  unsigned char nseg[32];
+  unsigned nsurv, lost;                   // allocation counter; owners that lost a candidate to a full pool
+};
+
+__device__ __forceinline__ void knn_insert(unsigned long long key, Knn5& k) {
+  if (key < k.k[4]) {
+    k.k[4] = key;
+#pragma unroll
+    for (int m = 4; m > 0; --m) {
+      const unsigned long long a = k.k[m - 1], b = k.k[m];
+      k.k[m - 1] = a < b ? a : b; k.k[m] = a < b ? b : a;
+    }
+  }
+}
+
+// d2 of a pooled candidate to its owner's query, and whether it passes the owner's bound
+__device__ __forceinline__ bool pool_test(const float4& pt, float qx, float qy, float qz, float ub, unsigned long long* key) {
+  const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+  *key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(pt.w);
+  return d2 < 1.0f && d2 <= ub;
+}
+
+__global__ void __launch_bounds__(kAssocThreads, 16) k_associate_pool(DevBuffers d, int lane0, int outer_it, int force,
+                                                                                  const double* pose_override, int shard_rank, int shard_world) {
+  const DevParams& p = d.p;
+  const int lane_b = lane0 + blockIdx.y;
+  const OdomState& os = d.ostate[lane_b];
+  const bool active = force || os.init;
+  const int share = shard_world > 1 ? (((os.n_edges + shard_world - 1) / shard_world + 31) & ~31) : 0;
+  const int E = shard_world > 1 ? min(os.n_edges, (shard_rank + 1) * share) : os.n_edges;
+  const int t = shard_rank * share + blockIdx.x * kAssocThreads + threadIdx.x;
+  const int ln = threadIdx.x & 31;
+  __shared__ PoolWarp smw[kAssocThreads / 32];
+  if (active && (t - ln) < E) {   // warp-uniform
+    PoolWarp& sm = smw[threadIdx.x >> 5];
+    const WinState& ws = d.wstate[lane_b];
+    const double* T = pose_override ? pose_override : os.odom;
+    const bool mine = t < E;
+    const int e = (mine && !force) ? d.perm[(size_t)lane_b * p.Ecap + t] : t;
+    const float4 c = mine ? d.edges[(size_t)lane_b * p.Ecap + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qx = xform_row(T, c.x, c.y, c.z), qy = xform_row(T + 4, c.x, c.y, c.z), qz = xform_row(T + 8, c.x, c.y, c.z);
+    const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
+    const unsigned hmask = (unsigned)p.Hcap - 1u, bmask = (unsigned)p.Bwords - 1u;
+    const HashEntry* tab = d.htab + (size_t)lane_b * p.Hcap;
+    const float4* sorted = d.sorted + (size_t)lane_b * p.Pcap;
+    const unsigned* bloom = d.bloom + (size_t)lane_b * p.Bwords;
+    Knn5 k;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) k.k[r] = kEmptyCand;
+    const bool searchable = mine && ws.hash_points > 0 && isfinite(qx) && isfinite(qy) && isfinite(qz);
+    const int cx = cell_of(qx), cy = cell_of(qy), cz = cell_of(qz);
+    // ---- phase A
+    int nseg = 0;
+    unsigned listed = 0;
+    // Second outer iteration (src/laser_odometry.cc:198): the map is the same as in the first and the pose moved by
+    // millimetres, so the five neighbours found then (still in knn_out) are five map points close to this query and the
+    // largest of their distances bounds the 5th-best distance from above.  With a bound in hand from the start nothing
+    // is scanned in place: the own cell is listed like the others and the whole search runs pooled.
+    float seed = 3.0e38f;
+    if (searchable && outer_it == 1 && !force && shard_world == 1) {
+      const int* prev = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+      if (prev[0] >= 0) {
+        const float4* lin = d.lin + (size_t)lane_b * p.LinCap;
+        const unsigned lmask = (unsigned)p.LinCap - 1u;
+        float m = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const float4 pt = lin[(unsigned)prev[r] & lmask];
+          const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
+          m = fmaxf(m, __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
+        }
+        if (m == m) seed = m;   // not NaN
+      }
+    }
+    const bool seeded = seed < 3.0e38f;
+    if (searchable) {
+      unsigned occ = 0;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) occ |= bloom_row(bloom, bmask, cx - 1, 3, cy + r % 3 - 1, cz + r / 3 - 1) << (3 * r);
+      const uint2 own = hash_lookup(tab, hmask, gen, cx, cy, cz);   // in flight together with the occupancy words
+      const int nx = __fsub_rn(qx, kCell * (float)cx) < 0.5f * kCell ? -1 : 1;
+      const int ny = __fsub_rn(qy, kCell * (float)cy) < 0.5f * kCell ? -1 : 1;
+      const int nz = __fsub_rn(qz, kCell * (float)cz) < 0.5f * kCell ? -1 : 1;
+      occ = occ_canonical(occ | (1u << 13), nx, ny, nz);
+      for (int i = 0; i < 27 && occ; ++i) {   // slot 0 = the own cell: one scan site for all in-place scans (code size)
+        const unsigned bit = kNearMask[i];
+        if (!(occ & bit)) continue;
+        occ &= ~bit;
+        const unsigned code = kNearOrder[i];
+        const int ax = code & 3, ay = (code >> 2) & 3, az = code >> 4;
+        const int dx = ax == 0 ? 0 : (ax == 1 ? nx : -nx), dy = ay == 0 ? 0 : (ay == 1 ? ny : -ny), dz = az == 0 ? 0 : (az == 1 ? nz : -nz);
+        uint2 sc = own;
+        if (i > 0) {
+          const float dmin = cell_min_d2(qx, qy, qz, cx + dx, cy + dy, cz + dz);
+          if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > seed) continue;
+          sc = hash_lookup(tab, hmask, gen, cx + dx, cy + dy, cz + dz);
+        }
+        if (sc.y == 0u) continue;
+        if ((k.k[4] == kEmptyCand && !seeded) || nseg == kPoolSegs) {
+          knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, seed, k);   // no bound yet (or list full)
+        } else {
+          sm.seg[nseg][ln] = sc; ++nseg; listed += sc.y;
+        }
+      }
+    }
+    // ---- phase B
+    sm.qx[ln] = qx; sm.qy[ln] = qy; sm.qz[ln] = qz;
+    // listed > 0 only with a bound in hand: five candidates, or the seed
+    sm.ub[ln] = k.k[4] == kEmptyCand ? seed : fminf(seed, __uint_as_float((unsigned)(k.k[4] >> 32)));
+    sm.nseg[ln] = (unsigned char)nseg;
+    sm.head[ln] = kPoolNil;
+    unsigned incl = listed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (ln >= o) incl += v; }
+    sm.pre[ln + 1] = incl;
+    if (ln == 0) { sm.pre[0] = 0u; sm.nsurv = 0u; sm.lost = 0u; }
+    __syncwarp();
+    const unsigned total = sm.pre[32];
+    if (total) {   // warp-uniform
+      const unsigned per = (total + 31u) >> 5;
+      const unsigned pos = (unsigned)ln * per;
+      unsigned rem = pos < total ? min(per, total - pos) : 0u;
+      if (rem) {
+        int o = 0;   // the owner whose listed range holds `pos`: the largest o with pre[o] <= pos
+#pragma unroll
+        for (int step = 16; step; step >>= 1) if (sm.pre[o + step] <= pos) o += step;
+        unsigned off = pos - sm.pre[o];
+        int s = 0;
+        uint2 sg = sm.seg[0][o];
+        while (off >= sg.y) { off -= sg.y; ++s; sg = sm.seg[s][o]; }
+        unsigned j = sg.x + off, jend = sg.x + sg.y;
+        float ox = sm.qx[o], oy = sm.qy[o], oz = sm.qz[o], oub = sm.ub[o];
+        int ons = sm.nseg[o];
+        while (rem) {
+          if (j == jend) {   // next listed bucket of this owner, else of the next owner that listed any
+            if (++s == ons) {
+              do { ++o; ons = sm.nseg[o]; } while (ons == 0);
+              s = 0; ox = sm.qx[o]; oy = sm.qy[o]; oz = sm.qz[o]; oub = sm.ub[o];
+            }
+            sg = sm.seg[s][o]; j = sg.x; jend = sg.x + sg.y;
+          }
+          const unsigned n = min(min(jend - j, rem), 4u), last = j + n - 1u;
+          const float4 p0 = __ldg(sorted + j), p1 = __ldg(sorted + min(j + 1u, last));
+          const float4 p2 = __ldg(sorted + min(j + 2u, last)), p3 = __ldg(sorted + min(j + 3u, last));
+          unsigned long long key[4];
+          bool ok[4];
+          ok[0] = pool_test(p0, ox, oy, oz, oub, &key[0]);
+          ok[1] = pool_test(p1, ox, oy, oz, oub, &key[1]) && n > 1u;
+          ok[2] = pool_test(p2, ox, oy, oz, oub, &key[2]) && n > 2u;
+          ok[3] = pool_test(p3, ox, oy, oz, oub, &key[3]) && n > 3u;
+          const unsigned cnt = (unsigned)ok[0] + (unsigned)ok[1] + (unsigned)ok[2] + (unsigned)ok[3];
+          if (cnt) {   // one allocation and one list splice for the (up to four) candidates of this owner
+            const unsigned base = atomicAdd(&sm.nsurv, cnt);
+            if (base + cnt <= (unsigned)kPoolSurv) {
+              unsigned slot = base;
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+                if (ok[r]) { sm.surv[slot] = key[r]; if (slot != base) sm.next[slot] = (unsigned short)(slot - 1u); ++slot; }
+              sm.next[base] = (unsigned short)atomicExch(&sm.head[o], base + cnt - 1u);
+            } else {
+              atomicOr(&sm.lost, 1u << o);
+            }
+          }
+          j += n; rem -= n;
+        }
+      }
+      __syncwarp();
+      // ---- phase C
+      if ((sm.lost >> ln) & 1u) {
+        for (int s = 0; s < nseg; ++s) {   // rare (a few % of the warps): a plain loop keeps the code small
+          const uint2 sg = sm.seg[s][ln];
+          for (unsigned j = 0; j < sg.y; ++j) knn_offer(__ldg(sorted + sg.x + j), qx, qy, qz, 3.0e38f, k);
+        }
+      } else {
+        for (unsigned sl = sm.head[ln]; sl != kPoolNil; sl = sm.next[sl]) knn_insert(sm.surv[sl], k);
+      }
+      __syncwarp();
+    }
+    knn_fallback_warp(tab, sorted, bloom, hmask, bmask, gen, searchable, qx, qy, qz, cx, cy, cz, k, ln);
+    if (mine) {
+      int* nn_out = d.knn_out + ((size_t)lane_b * p.Ecap + e) * 5;
+#pragma unroll
+      for (int r = 0; r < 5; ++r) nn_out[r] = k.k[4] == kEmptyCand ? -1 : (int)(unsigned)k.k[r];
+      if (d.gate) {
+        const size_t o = (size_t)lane_b * p.Ecap + e;
+        for (int r = 0; r < 5; ++r) {
+          d.knn_idx[o * 5 + r] = k.k[r] == kEmptyCand ? -1 : (int)((unsigned)k.k[r] - win_g0(d, lane_b));   // logical index
+          d.knn_d2[o * 5 + r] = k.k[r] == kEmptyCand ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(k.k[r] >> 32));
+        }
+        d.q_world[o] = make_float4(qx, qy, qz, c.w);
+      }
     }
   }
   if (active && blockIdx.x == 0 && threadIdx.x == 0) d.diag[lane_b].n_map[outer_it] = d.wstate[lane_b].hash_points;
@@ -1232,7 +1474,14 @@ static void launch_associate_any(const DevBuffers& d, cudaStream_t s, int lane0,
     // list insertions run with 5 of 32 lanes and its barriers cost occupancy; profiles/k_associate_cta_r02d_lanes128.txt)
     const char* cta_env = getenv("LIODOM_ASSOC_CTA");
     const bool per_thread = !(cta_env && atoi(cta_env) == 1);
-    if (per_thread) k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+    // The warp-pooled kernel is used where it wins: the second outer iteration, whose bound is seeded from the first
+    // one's neighbours so that the whole search runs pooled (ncu at 128 lanes: 382 vs 446 us, 19 vs 11 active threads;
+    // unseeded it is 463 vs 441 us — 64 registers and 10 KB of shared memory per CTA cost occupancy;
+    // profiles/k_associate_pool_r02q_lanes128.txt).  LIODOM_ASSOC_POOL=0 / 1 forces never / always.
+    const char* pool_env = getenv("LIODOM_ASSOC_POOL");
+    const bool pooled = pool_env ? atoi(pool_env) == 1 : (outer_it == 1 && !force && world == 1);
+    if (pooled && per_thread) k_associate_pool<<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
+    else if (per_thread) k_associate<1><<<g, kAssocThreads, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
     else k_associate_cta<<<dim3((edges_per_lane + kCtaQ - 1) / kCtaQ, nlanes), kCtaQ, 0, s>>>(d, lane0, outer_it, force, pose_override, rank, world);
     k_line_gate<<<dim3((edges_per_lane + 127) / 128, nlanes), 128, 0, s>>>(d, lane0, outer_it, force, rank, world);
   }

@@ -77,8 +77,16 @@ SharedData* SharedData::getInstance() {
 // Both queues share one shape: the cloud pointer and its header travel together, nothing is copied.
 template <typename F>
 static void fifo_push(F& q, const PointCloud::Ptr& cloud, const Header& header) {
-  std::lock_guard<std::mutex> lock(q.m);
-  q.items.push(cloud); q.headers.push(header);
+  {
+    std::lock_guard<std::mutex> lock(q.m);
+    q.items.push(cloud); q.headers.push(header);
+  }
+  q.cv.notify_one();
+}
+template <typename F>
+static void fifo_wait(F& q, int ms) {
+  std::unique_lock<std::mutex> lock(q.m);
+  q.cv.wait_for(lock, std::chrono::milliseconds(ms), [&] { return !q.items.empty(); });
 }
 template <typename F>
 static bool fifo_pop(F& q, PointCloud::Ptr& cloud, Header& header) {
@@ -92,6 +100,8 @@ void SharedData::pushPointCloud(const PointCloud::Ptr& pc_in, const Header& head
 bool SharedData::popPointCloud(PointCloud::Ptr& pc_out, Header& header) { return fifo_pop(scans_, pc_out, header); }
 void SharedData::pushFeatures(const PointCloud::Ptr& feat_in, Header& header) { fifo_push(feats_, feat_in, header); }
 bool SharedData::popFeatures(PointCloud::Ptr& feat_out, Header& header) { return fifo_pop(feats_, feat_out, header); }
+void SharedData::waitPointCloud(int ms) { fifo_wait(scans_, ms); }
+void SharedData::waitFeatures(int ms) { fifo_wait(feats_, ms); }
 void SharedData::setLocalMap(const PointCloud::Ptr& map_in) {
   std::lock_guard<std::mutex> lock(map_mutex_);
   *local_map_ = *map_in;   // pcl::copyPointCloud: deep copy
@@ -310,7 +320,7 @@ void FeatureExtractor::operator()(std::atomic<bool>& running) {
       if (edges_cb_) edges_cb_(pc_header, pc_edges);
       sdata->pushFeatures(pc_edges, pc_header);
     }
-    std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    sdata->waitPointCloud(2);   // the reference sleeps 2 ms here (src/feature_extractor.cc:80); see shared_data.h
   }
 }
 
@@ -592,7 +602,7 @@ void LaserOdometer::operator()(std::atomic<bool>& running) {
         publishOdom(feat_header, odom_);
       }
     }
-    std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    sdata->waitFeatures(2);   // the reference sleeps 2 ms here (src/laser_odometry.cc:270); see shared_data.h
   }
 }
 
@@ -710,7 +720,7 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
     if (opt->lockstep) {
       const auto t0 = Clock::now();
       while (produced.load() <= f && std::chrono::duration_cast<std::chrono::seconds>(Clock::now() - t0).count() < 30)
-        std::this_thread::sleep_for(std::chrono::microseconds(200));
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
   }
   const auto t0 = Clock::now();

@@ -97,6 +97,15 @@ def test_batch128_cta_level_association(cuda_lib, monkeypatch):
     print("batch 128, CTA-level association: worst pose error %.3g m %.3g rad" % (w[0], w[1]))
 
 
+@pytest.mark.parametrize("pool", ["0", "1"])
+def test_batch128_warp_pooled_association(cuda_lib, pool, monkeypatch):
+    """LIODOM_ASSOC_POOL=0 / 1: the thread-per-edge kernel in both outer iterations / the warp-pooled one in both (the
+    default is thread-per-edge first, pooled and seeded second: every other test of this file).  Same poses."""
+    monkeypatch.setenv("LIODOM_ASSOC_POOL", pool)
+    w = _run_batch(128, "device")
+    print("batch 128, LIODOM_ASSOC_POOL=%s: worst pose error %.3g m %.3g rad" % (pool, w[0], w[1]))
+
+
 @pytest.mark.parametrize("name", ["c2_ouster", "c3_stress"])
 def test_batch_other_baseline_shapes(cuda_lib, name):
     """The other BASELINE.json shapes through the batched path with a full window (the incremental voxel hash with

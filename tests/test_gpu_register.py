@@ -81,13 +81,17 @@ def _teacher_forced_associate(ctx, edges_seq, gt, K):
     return nchecked
 
 
-@pytest.mark.parametrize("group", ["1", "4", "8", "16", "cta"])
+@pytest.mark.parametrize("group", ["1", "4", "8", "16", "cta", "pool", "thread"])
 def test_associate_teacher_forced_c1(cuda_lib, group, monkeypatch):
-    """Every kernel variant (1, 4, 8 or 16 threads per edge; picked by the number of edges in flight) and the opt-in
-    CTA-level variant of the one-thread-per-edge search (LIODOM_ASSOC_CTA=1)."""
+    """Every kernel variant (1, 4, 8 or 16 threads per edge; picked by the number of edges in flight), the warp-pooled
+    form of the one-thread-per-edge search (LIODOM_ASSOC_POOL=1 / 0) and the opt-in CTA-level one (LIODOM_ASSOC_CTA=1)."""
     monkeypatch.delenv("LIODOM_ASSOC_CTA", raising=False)
+    monkeypatch.delenv("LIODOM_ASSOC_POOL", raising=False)
     if group == "cta":
         monkeypatch.setenv("LIODOM_ASSOC_CTA", "1")
+        group = "1"
+    elif group in ("pool", "thread"):
+        monkeypatch.setenv("LIODOM_ASSOC_POOL", "1" if group == "pool" else "0")
         group = "1"
     monkeypatch.setenv("LIODOM_ASSOC_GROUP", group)
     scans, gt = get_sequence("hdl64", 1000, 5)
