@@ -671,7 +671,9 @@ constexpr int kFbSide = 2 * kFbRadius + 1;
 
 __device__ __forceinline__ float axis_gap(float q, int cell) {
   const float lo = kCell * (float)cell, hi = lo + kCell;   // exact
-  return q < lo ? __fsub_rn(lo, q) : (q > hi ? __fsub_rn(q, hi) : 0.0f);
+  // q < lo: lo - q (and q - hi < 0); q > hi: q - hi (and lo - q < 0); inside: both <= 0.  Branch-free; the compiler
+  // turned the conditional form into divergent branches inside the neighbour loops.
+  return fmaxf(fmaxf(__fsub_rn(lo, q), __fsub_rn(q, hi)), 0.0f);
 }
 
 __device__ __forceinline__ void knn_offer(const float4& pt, float qx, float qy, float qz, float ub, Knn5& k) {
@@ -838,28 +840,27 @@ __device__ __forceinline__ bool line_gate(const DevBuffers& d, int lane_b, int e
 
 constexpr int kAssocThreads = 64;
 
-// Visit order of the 27 cells of a cube: per axis 0 = own cell, 1 = the neighbour behind the nearer
-// face, 2 = the one behind the farther face; sorted by sum of weights (0, 1, 4).  Entry = ax | ay << 2 | az << 4.
-__constant__ unsigned char kNearOrder[27] = {
-    0x00,                                     // (0,0,0)
-    0x01, 0x04, 0x10,                         // one near
-    0x05, 0x11, 0x14,                         // two near
-    0x15,                                     // three near
-    0x02, 0x08, 0x20,                         // one far
-    0x06, 0x09, 0x12, 0x18, 0x21, 0x24,       // one far + one near
-    0x16, 0x19, 0x25,                         // one far + two near
-    0x0a, 0x22, 0x28,                         // two far
-    0x1a, 0x26, 0x29,                         // two far + one near
-    0x2a};                                    // three far
-
-// The same order on the CANONICAL occupancy word: occ_canonical reflects every axis whose near side is +1, so that
-// "near" is offset -1 for every lane and slot i of the order is one constant bit, bit = ((cz+1)*3 + (cy+1))*3 + (cx+1)
-// with c = 0 (own), -1 (near), +1 (far).  The slot test is then two instructions; the offsets are decoded only for
-// occupied slots (the per-slot decode was 10 % of k_associate<1>'s instructions).
+// Visit order of the 27 cells of a cube, nearest first: per axis the own cell, then the neighbour behind the nearer face,
+// then the one behind the farther face; slots sorted by the sum of the per-axis weights (0, 1, 4): own; one near (3);
+// two near (3); three near; one far (3); one far + one near (6); one far + two near (3); two far (3); two far + one
+// near (3); three far.  The bound tightens before the far cells are looked at and most of them fall to cell_min_d2.
+// The order is applied to the CANONICAL occupancy word: occ_canonical reflects every axis whose near side is +1, so that
+// "near" is offset -1 for every lane and slot i is one constant bit, bit = ((cz+1)*3 + (cy+1))*3 + (cx+1) with c = 0
+// (own), -1 (near), +1 (far).  The slot test is then two instructions and the offsets are decoded only for occupied
+// slots, by arithmetic (a per-slot ?: decode compiled to indirect branches and was 10 % of k_associate<1>).
 __constant__ unsigned kNearMask[27] = {
     0x0002000, 0x0001000, 0x0000400, 0x0000010, 0x0000200, 0x0000008, 0x0000002, 0x0000001, 0x0004000,
     0x0010000, 0x0400000, 0x0000800, 0x0008000, 0x0000020, 0x0000080, 0x0200000, 0x0080000, 0x0000004,
     0x0000040, 0x0040000, 0x0020000, 0x0800000, 0x2000000, 0x0000100, 0x0100000, 0x1000000, 0x4000000};
+// Cell offsets of slot i: canonical (0 own, -1 near, +1 far; 2-bit two's complement fields x | y << 2 | z << 4) times the
+// lane's near direction.  Arithmetic only (the ?: form of the decode compiled to indirect branches).
+__constant__ unsigned char kNearOff[27] = {0, 3, 12, 48, 15, 51, 60, 63, 1, 4, 16, 13, 7, 49, 52, 19, 28, 61, 55, 31, 5, 17, 20, 53, 29, 23, 21};
+__device__ __forceinline__ void near_offsets(int i, int nx, int ny, int nz, int* dx, int* dy, int* dz) {
+  const int v = kNearOff[i];
+  *dx = -(((v << 30) >> 30) * nx);
+  *dy = -(((v << 28) >> 30) * ny);
+  *dz = -(((v << 26) >> 30) * nz);
+}
 __device__ __forceinline__ unsigned occ_canonical(unsigned occ, int nx, int ny, int nz) {
   if (nx > 0) occ = ((occ & 0x1249249u) << 2) | ((occ & 0x4924924u) >> 2) | (occ & 0x2492492u);
   if (ny > 0) occ = ((occ & 0x01c0e07u) << 6) | ((occ & 0x70381c0u) >> 6) | (occ & 0x0e07038u);
@@ -927,9 +928,8 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
           const unsigned bit = kNearMask[i];
           if (!(occ & bit)) continue;
           occ &= ~bit;
-          const unsigned code = kNearOrder[i];
-          const int ax = code & 3, ay = (code >> 2) & 3, az = code >> 4;
-          const int dx = ax == 0 ? 0 : (ax == 1 ? nx : -nx), dy = ay == 0 ? 0 : (ay == 1 ? ny : -ny), dz = az == 0 ? 0 : (az == 1 ? nz : -nz);
+          int dx, dy, dz;
+          near_offsets(i, nx, ny, nz, &dx, &dy, &dz);
           knn_scan_cell(tab, sorted, hmask, gen, cx + dx, cy + dy, cz + dz, qx, qy, qz, 3.0e38f, k);
         }
       }
@@ -1115,9 +1115,8 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate_pool(DevBuffers
         const unsigned bit = kNearMask[i];
         if (!(occ & bit)) continue;
         occ &= ~bit;
-        const unsigned code = kNearOrder[i];
-        const int ax = code & 3, ay = (code >> 2) & 3, az = code >> 4;
-        const int dx = ax == 0 ? 0 : (ax == 1 ? nx : -nx), dy = ay == 0 ? 0 : (ay == 1 ? ny : -ny), dz = az == 0 ? 0 : (az == 1 ? nz : -nz);
+        int dx, dy, dz;
+        near_offsets(i, nx, ny, nz, &dx, &dy, &dz);
         uint2 sc = own;
         if (i > 0) {
           const float dmin = cell_min_d2(qx, qy, qz, cx + dx, cy + dy, cz + dz);
