@@ -660,11 +660,13 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
 // Empty cells cost no hash probe: an occupancy filter (one bit per cell, 32 x-consecutive cells per
 // word, word = hash(ix >> 5, iy, iz)) is read one row at a time; a false positive costs one probe.
 // Sorted 5-list of packed candidates (float bits of d2) << 32 | logical index: d2 >= 0, so the
-// unsigned 64-bit order is the (d2, index) order.  Empty entries are ~0.
+// unsigned 64-bit order is the (d2, index) order.
 struct Knn5 {
   unsigned long long k[5];
 };
-constexpr unsigned long long kEmptyCand = ~0ull;
+// Empty entries are (bits of 1.0f) << 32: above every admissible candidate (d2 < 1.0, src/laser_odometry.cc:324 gates on
+// the 5th distance), so `key < k[4]` is also the d2 < 1.0 test and an empty list prunes cells beyond the 1 m radius.
+constexpr unsigned long long kEmptyCand = 0x3f80000000000000ull;
 constexpr float kProvenD2 = kCell * kCell;   // 5th-best below this: the 27-cell cube was enough
 constexpr int kFbRadius = (int)(1.0f / kCell);   // cells covering the 1 m gate radius
 constexpr int kFbSide = 2 * kFbRadius + 1;
@@ -676,18 +678,26 @@ __device__ __forceinline__ float axis_gap(float q, int cell) {
   return fmaxf(fmaxf(__fsub_rn(lo, q), __fsub_rn(q, hi)), 0.0f);
 }
 
+// Sorted insertion of a key known to be below k[4]: four INDEPENDENT comparisons against the old entries, then every
+// new entry is a two-level select (8 compare + 16 select instructions; the compare-exchange chain compiled to an LT and
+// a GT comparison per stage, 34 instructions, and the insertion is a quarter of the search kernels' instructions).
+__device__ __forceinline__ void knn_place(unsigned long long key, unsigned long long* k) {
+  const bool c0 = key < k[0], c1 = key < k[1], c2 = key < k[2], c3 = key < k[3];
+  const unsigned long long t0 = c0 ? k[0] : key, t1 = c1 ? k[1] : key, t2 = c2 ? k[2] : key, t3 = c3 ? k[3] : key;
+  k[4] = t3;
+  k[3] = c3 ? t2 : k[3];
+  k[2] = c2 ? t1 : k[2];
+  k[1] = c1 ? t0 : k[1];
+  k[0] = c0 ? key : k[0];
+}
+
 __device__ __forceinline__ void knn_offer(const float4& pt, float qx, float qy, float qz, float ub, Knn5& k) {
   // flann::L2_Simple<float>: result += diff*diff over x, y, z in float
   const float ddx = __fsub_rn(qx, pt.x), ddy = __fsub_rn(qy, pt.y), ddz = __fsub_rn(qz, pt.z);
   const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
   const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(pt.w);
-  if (d2 < 1.0f && d2 <= ub && key < k.k[4]) {
-    k.k[4] = key;
-#pragma unroll
-    for (int m = 4; m > 0; --m) {
-      const unsigned long long a = k.k[m - 1], b = k.k[m];
-      k.k[m - 1] = a < b ? a : b; k.k[m] = a < b ? b : a;
-    }
+  if (d2 <= ub && key < k.k[4]) {
+    knn_place(key, k.k);
   }
 }
 
@@ -734,7 +744,7 @@ __device__ __forceinline__ void knn_scan_cell(const HashEntry* __restrict__ tab,
                                               unsigned hmask, unsigned gen, int ix, int iy, int iz,
                                               float qx, float qy, float qz, float ub, Knn5& k) {
   const float dmin = cell_min_d2(qx, qy, qz, ix, iy, iz);
-  if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
+  if (__float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) return;
   const uint2 sc = hash_lookup(tab, hmask, gen, ix, iy, iz);
   knn_scan_bucket(sorted + sc.x, sc.y, qx, qy, qz, ub, k);
 }
@@ -745,7 +755,7 @@ __device__ __forceinline__ void knn_scan_row(const HashEntry* __restrict__ tab, 
                                              int ix0, int n, unsigned skip, int iy, int iz,
                                              float qx, float qy, float qz, float ub, Knn5& k) {
   const float g2 = sq_sum2(axis_gap(qy, iy), axis_gap(qz, iz));
-  if (g2 >= 1.0f || __float_as_uint(g2) > (unsigned)(k.k[4] >> 32) || g2 > ub) return;
+  if (__float_as_uint(g2) > (unsigned)(k.k[4] >> 32) || g2 > ub) return;
   unsigned mask = bloom_row(bloom, bmask, ix0, n, iy, iz) & ~skip;
   while (mask) {
     const int bsel = __ffs(mask) - 1;
@@ -768,7 +778,7 @@ __device__ __forceinline__ void knn_fallback_warp(const HashEntry* __restrict__ 
     const float jx = __shfl_sync(0xffffffffu, qx, owner), jy = __shfl_sync(0xffffffffu, qy, owner), jz = __shfl_sync(0xffffffffu, qz, owner);
     const int jcx = __shfl_sync(0xffffffffu, cx, owner), jcy = __shfl_sync(0xffffffffu, cy, owner), jcz = __shfl_sync(0xffffffffu, cz, owner);
     const unsigned ubb = __shfl_sync(0xffffffffu, (unsigned)(k.k[4] >> 32), owner);
-    const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
+    const float ub = __uint_as_float(ubb);   // 1.0 when the list is not full yet
     Knn5 l;
 #pragma unroll
     for (int r = 0; r < 5; ++r) {   // lane 0 inherits the owner's list, the others start empty
@@ -941,7 +951,7 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
         for (unsigned j = gl; j < sc.y; j += G) knn_offer(__ldg(sorted + sc.x + j), qx, qy, qz, 3.0e38f, k);
       }
       const unsigned ubb = __reduce_min_sync(gmask, (unsigned)(k.k[4] >> 32));
-      const float ub = ubb == 0xffffffffu ? 3.0e38f : __uint_as_float(ubb);
+      const float ub = __uint_as_float(ubb);   // 1.0 when the list is not full yet
       if (searchable)
         for (int r = gl; r < 9; r += G)
           knn_scan_row(tab, sorted, bloom, hmask, bmask, gen, cx - 1, 3, r == 4 ? 2u : 0u, cy + r % 3 - 1, cz + r / 3 - 1, qx, qy, qz, ub, k);
@@ -1032,12 +1042,7 @@ struct PoolWarp {
 
 __device__ __forceinline__ void knn_insert(unsigned long long key, Knn5& k) {
   if (key < k.k[4]) {
-    k.k[4] = key;
-#pragma unroll
-    for (int m = 4; m > 0; --m) {
-      const unsigned long long a = k.k[m - 1], b = k.k[m];
-      k.k[m - 1] = a < b ? a : b; k.k[m] = a < b ? b : a;
-    }
+    knn_place(key, k.k);
   }
 }
 
@@ -1120,7 +1125,7 @@ __global__ void __launch_bounds__(kAssocThreads, 16) k_associate_pool(DevBuffers
         uint2 sc = own;
         if (i > 0) {
           const float dmin = cell_min_d2(qx, qy, qz, cx + dx, cy + dy, cz + dz);
-          if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > seed) continue;
+          if (__float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > seed) continue;
           sc = hash_lookup(tab, hmask, gen, cx + dx, cy + dy, cz + dz);
         }
         if (sc.y == 0u) continue;
@@ -1364,7 +1369,7 @@ __global__ void __launch_bounds__(kCtaQ, 8) k_associate_cta(DevBuffers d, int la
         const int b = __ffs(rest) - 1;
         const int dz = b / 9 - 1, r9 = b - 9 * (dz + 1), dy = r9 / 3 - 1, dx = r9 - 3 * (dy + 1) - 1;
         const float dmin = cell_min_d2(qx, qy, qz, cx + dx, cy + dy, cz + dz);
-        if (dmin >= 1.0f || __float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) continue;
+        if (__float_as_uint(dmin) > (unsigned)(k.k[4] >> 32) || dmin > ub) continue;
         const uint2 sc = hash_lookup(tab, hmask, gen, cx + dx, cy + dy, cz + dz);
         if (sc.y == 0u) continue;
         if (nseg < kSegCap) { sm.seg[nseg][u] = sc; ++nseg; work += sc.y; }
