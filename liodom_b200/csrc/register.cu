@@ -636,6 +636,31 @@ __device__ void sym3_eigenvalues(double a00, double a01, double a02, double a11,
   w[0] = e0; w[1] = e1; w[2] = e2;
 }
 
+// Screen of the line gate lambda2 > 3 lambda1 (src/laser_odometry.cc:344) that skips the ~1300 FP64 instructions of the
+// Jacobi sweeps for almost every edge: eigenvalues of the symmetric 3x3 from the trigonometric closed form
+// (q = tr/3, p = sqrt(|A - qI|_F^2 / 6), r = det((A - qI)/p)/2, phi = acos(r)/3, lambda = q + 2p cos(phi + 2k pi/3)).
+// Its error is <= ~1e-8 lambda2 even where two eigenvalues coincide (acos near +-1 amplifies the rounding of r by
+// 1/sqrt(eps)); the Jacobi values are within 1e-13 |A| of the true ones.  The decision is taken here only when
+// |lambda2 - 3 lambda1| > 1e-5 lambda2, three orders of magnitude beyond both errors, so it is the decision the Jacobi
+// values give; otherwise (returns -1: ~1e-5 of the edges, degenerate scatter, NaN) the exact path decides.
+// In debug mode (per-edge outputs requested) both run and a disagreement is flagged in the gate byte (bit 2).
+__device__ __forceinline__ int sym3_gate_screen(double a00, double a01, double a02, double a11, double a12, double a22) {
+  const double q = (a00 + a11 + a22) * (1.0 / 3.0);
+  const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+  const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * (a01 * a01 + a02 * a02 + a12 * a12);
+  if (!(p2 > 0.0)) return -1;
+  const double p = sqrt(p2 * (1.0 / 6.0)), ip = 1.0 / p;
+  const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+  r = fmin(1.0, fmax(-1.0, r));
+  const double phi = acos(r) * (1.0 / 3.0);
+  const double l2 = q + 2.0 * p * cos(phi);
+  const double l0 = q + 2.0 * p * cos(phi + 2.0943951023931953);
+  const double l1 = 3.0 * q - l2 - l0;
+  const double dd = l2 - 3.0 * l1, margin = 1e-5 * l2;
+  return dd > margin ? 1 : (dd < -margin ? 0 : -1);
+}
+
 // A.1: float(m0*x + m1*y + m2*z + m3), double, left to right
 __device__ __forceinline__ float xform_row(const double* m, double x, double y, double z) {
   return __double2float_rn(ADD(ADD(ADD(MUL(m[0], x), MUL(m[1], y)), MUL(m[2], z)), m[3]));
@@ -834,8 +859,14 @@ __device__ __forceinline__ bool line_gate(const DevBuffers& d, int lane_b, int e
       c00 = ADD(c00, MUL(dx, dx)); c01 = ADD(c01, MUL(dx, dy)); c02 = ADD(c02, MUL(dx, dz));
       c11 = ADD(c11, MUL(dy, dy)); c12 = ADD(c12, MUL(dy, dz)); c22 = ADD(c22, MUL(dz, dz));
     }
-    sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
-    if (ev[2] > MUL(3.0, ev[1])) { gt |= 2; a = nn[0]; b = nn[1]; }  // :344, :351-357
+    const int screen = sym3_gate_screen(c00, c01, c02, c11, c12, c22);
+    bool pass = screen == 1;
+    if (screen < 0 || d.gate) {
+      sym3_eigenvalues(c00, c01, c02, c11, c12, c22, ev);
+      pass = ev[2] > MUL(3.0, ev[1]);   // :344
+      if (screen >= 0 && (screen == 1) != pass) gt |= 4;   // debug: the screen must never disagree
+    }
+    if (pass) { gt |= 2; a = nn[0]; b = nn[1]; }  // :351-357
   }
   float* blk = d.blocks + ((size_t)lane_b * p.Ecap + e) * 10;
   blk[0] = c.x; blk[1] = c.y; blk[2] = c.z; blk[3] = a.x; blk[4] = a.y; blk[5] = a.z;

@@ -1070,6 +1070,9 @@ void orc_associate(const float* edges_xyzi, int E, const double* T, const float*
                        knn_idx, knn_d2, gate, eig, q_world, tie);
 }
 
+/* A.6 alone: eigenvalues (ascending) of a symmetric 3x3, row-major; used to check the GPU line-gate screen. */
+void orc_sym3_eigenvalues(const double* A9, double* w3) { sym3_eigenvalues(A9, w3); }
+
 void orc_factor(const double* c, const double* a, const double* b, double min_range, double max_range,
                 const double* q, const double* t, double* r3, double* J18) {
   factor_eval(c, a, b, min_range, max_range, q, t, r3, J18);

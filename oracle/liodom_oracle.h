@@ -91,6 +91,10 @@ void orc_associate(const float* edges_xyzi, int E, const double* T, const float*
 /* A9 Point2LineFactor (include/liodom/factors.hpp:64-121): residual (3) and the 3x6
  * tangent Jacobian (row-major, cols = 3 quaternion-local then 3 translation) that
  * Ceres' autodiff + EigenQuaternionParameterization yields. q = (x,y,z,w). */
+/* Eigenvalues (ascending) of a symmetric 3x3 (row-major 9 doubles): the cyclic Jacobi that stands in for
+ * Eigen::SelfAdjointEigenSolver in the line gate (src/laser_odometry.cc:341-344). */
+void orc_sym3_eigenvalues(const double* A9, double* w3);
+
 void orc_factor(const double* c, const double* a, const double* b, double min_range, double max_range,
                 const double* q, const double* t, double* r3, double* J18);
 
