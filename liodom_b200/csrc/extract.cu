@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(256) k_split_count(DevBuffers d, int lane0) {
 }
 
 // Pass 2: exclusive scan over (ring-major, chunk) -> chunk_base, ring_off. grid B, 128 threads.
+// One thread per ring walks that ring's chunk counts; the loads are issued eight at a time (their addresses do not
+// depend on the running sum), which turns ~60 dependent round trips into ~8 (21 -> 5 us at 128 lanes).
 __global__ void __launch_bounds__(kMaxLines) k_split_scan(DevBuffers d, int lane0) {
   const int lane_b = lane0 + blockIdx.x;
   const DevParams& p = d.p;
@@ -192,12 +194,27 @@ __global__ void __launch_bounds__(kMaxLines) k_split_scan(DevBuffers d, int lane
   const ScanDesc sc = d.scan[lane_b];
   const int nch = (sc.n + kChunk - 1) / kChunk;
   __shared__ int tot[kMaxLines + 1];
+  __shared__ int s_amb;
+  if (r == 0) s_amb = 0;
+  __syncthreads();
   int run = 0;
   if (r < L) {
     const int* h = d.chunk_hist + (size_t)lane_b * p.chunks * L + r;
     int* b = d.chunk_base + (size_t)lane_b * p.chunks * L + r;
-    for (int c = 0; c < nch; ++c) { const int v = h[(size_t)c * L]; b[(size_t)c * L] = run; run += v; }
+    for (int c0 = 0; c0 < nch; c0 += 8) {
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c0 + k < nch ? h[(size_t)(c0 + k) * L] : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c0 + k < nch) { b[(size_t)(c0 + k) * L] = run; run += v[k]; }
+    }
     tot[r] = run;
+  }
+  {   // ambiguous-bin count of the scan: every thread sums a strided share of the chunks
+    int amb = 0;
+    for (int c = r; c < nch; c += blockDim.x) amb += d.chunk_amb[(size_t)lane_b * p.chunks + c];
+    if (amb) atomicAdd(&s_amb, amb);
   }
   __syncthreads();
   if (r == 0) {
@@ -206,9 +223,7 @@ __global__ void __launch_bounds__(kMaxLines) k_split_scan(DevBuffers d, int lane
     for (int k = 0; k < L; ++k) { off[k] = acc; acc += tot[k]; }
     off[L] = acc;
     d.ostate[lane_b].n_valid = acc;
-    int amb = 0;
-    for (int c = 0; c < nch; ++c) amb += d.chunk_amb[(size_t)lane_b * p.chunks + c];
-    d.ostate[lane_b].n_ambiguous = amb;
+    d.ostate[lane_b].n_ambiguous = s_amb;
   }
 }
 
