@@ -687,6 +687,8 @@ struct liodom_host_options {
 // Returns the number of poses produced, or a negative value on setup failure.
 }  // extern "C"
 
+static std::vector<double> g_run_push_ms, g_run_pose_ms;   // liodom_host_last_run_times()
+
 static int run_sequence_impl(const liodom_host_options* opt, int nframes, const std::function<liodom::PointCloud::Ptr(int)>& make_cloud,
                              double* poses_out, int* nfeats_out, const char* results_dir) {
   using namespace liodom;
@@ -704,9 +706,16 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
   LaserOdometer lodom(nh);
   std::atomic<int> produced(0);
   std::vector<int> nf((size_t)nframes, 0);
+  // Wall-clock marks of the run for liodom_host_last_run_times(): the reference's Stats keeps whole milliseconds
+  // (src/stats.cc:42-67), too coarse for sub-millisecond frames.
+  const auto run_t0 = Clock::now();
+  auto since_ms = [&]() { return std::chrono::duration<double, std::milli>(Clock::now() - run_t0).count(); };
+  g_run_push_ms.assign((size_t)nframes, 0.0);
+  g_run_pose_ms.assign((size_t)nframes, 0.0);
   fext.setEdgesCallback([&](const Header& h, const PointCloud::Ptr& e) { if ((int)h.seq < nframes) nf[h.seq] = (int)e->size(); });
   lodom.setOdomCallback([&](const Header& h, const Isometry3d& pose) {
     if ((int)h.seq < nframes && poses_out) detail::pose_to16(pose, poses_out + 16 * (size_t)h.seq);
+    if ((int)h.seq < nframes) g_run_pose_ms[h.seq] = since_ms();
     produced++;
   });
   std::atomic<bool> running(true);
@@ -716,6 +725,7 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
     PointCloud::Ptr pc = make_cloud(f);
     Header h; h.seq = (uint32_t)f; detail::set_stamp(h, 0.1 * f); h.frame_id = "laser";
     stats->startFrame(Clock::now());
+    g_run_push_ms[(size_t)f] = since_ms();
     sdata->pushPointCloud(pc, h);
     if (opt->lockstep) {
       const auto t0 = Clock::now();
@@ -735,6 +745,14 @@ static int run_sequence_impl(const liodom_host_options* opt, int nframes, const 
 }
 
 extern "C" {
+
+/* Per-frame wall-clock marks of the last liodom_host_run_sequence[_msgs] call, in milliseconds since its start: when
+ * the cloud was pushed and when its pose came out.  Returns the number of frames written (<= cap).  Harness only. */
+int liodom_host_last_run_times(double* push_ms, double* pose_ms, int cap) {
+  const int n = (int)std::min(g_run_push_ms.size(), (size_t)std::max(cap, 0));
+  for (int i = 0; i < n; ++i) { if (push_ms) push_ms[i] = g_run_push_ms[(size_t)i]; if (pose_ms) pose_ms[i] = g_run_pose_ms[(size_t)i]; }
+  return n;
+}
 
 int liodom_host_run_sequence(const liodom_host_options* opt, const float* scans, const int* npts, int nframes,
                              double* poses_out, int* nfeats_out, const char* results_dir) {

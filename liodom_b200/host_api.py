@@ -41,6 +41,15 @@ def run_sequence(scans, results_dir="", lockstep=True, width=0, height=0, **kw):
     return poses.reshape(-1, 4, 4), nf, produced
 
 
+def last_run_times(n):
+    """-> (push_ms [n], pose_ms [n]): wall-clock marks of the last run_sequence call, ms since its start."""
+    lib = load()
+    lib.liodom_host_last_run_times.restype = ctypes.c_int
+    push, pose = np.zeros(n), np.zeros(n)
+    m = lib.liodom_host_last_run_times(push.ctypes.data_as(ctypes.c_void_p), pose.ctypes.data_as(ctypes.c_void_p), n)
+    return push[:m], pose[:m]
+
+
 FLOAT32, UINT16, FLOAT64 = 7, 4, 8   # sensor_msgs/PointField datatypes
 
 
