@@ -81,7 +81,7 @@ __device__ __forceinline__ unsigned win_g0(const DevBuffers& d, int lane_b) {
 // voxel hash.  Table: open addressing on packed (ix, iy, iz, generation).  Buckets: contiguous runs of the pool
 // `sorted`, the points of a voxel in frame order (oldest first), w = sequence number.  `lin`: ring of the points
 // by sequence number.  Three ways to bring it up to date after the window changed (hash_begin picks one):
-//   incremental     k_hash_evict -> k_hash_add_count -> k_hash_grow -> k_hash_add_scatter      (~2 frames of work)
+//   incremental     k_hash_evict_add (eviction + new-frame count, one launch) -> k_hash_grow -> k_hash_add_scatter  (~2 frames of work)
 //   full, ordered   k_hash_full_ordered (one CTA per lane; rare)
 //   full, fast      k_bloom_clear -> k_hash_insert -> k_hash_alloc -> k_hash_scatter           (mapping / window filter)
 // Every kernel returns at once unless its mode is the chosen one, so the host enqueues a fixed sequence.
@@ -201,16 +201,17 @@ __global__ void __launch_bounds__(256) k_bloom_clear(DevBuffers d, int lane0) {
 
 // ---- incremental ---------------------------------------------------------------------------------------------
 // The evicted frame's points sit at the heads of their buckets (buckets are in frame order): advance the heads.
-__global__ void __launch_bounds__(256) k_hash_evict(DevBuffers d, int lane0) {
-  const int lane_b = lane0 + blockIdx.y;
+// Eviction and the new frame's first pass run in ONE launch (even / odd CTAs): both are chains of dependent loads at
+// < 25 % issue rate, eviction only touches the (start, count) of cells that exist, the new frame only creates cells and
+// counts in `newcnt`, so they commute and their latencies overlap (43 -> ~27 us at 128 lanes).
+__device__ __forceinline__ void hash_evict_part(const DevBuffers& d, int lane_b, int part, int nparts) {
   const WinState& ws = d.wstate[lane_b];
-  if (ws.hmode != kHashIncr) return;
   hash_check_generation(ws);
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned mask = (unsigned)d.p.Hcap - 1u;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   const float4* slab = d.win + ((size_t)lane_b * d.p.slots + ws.ev_slab) * d.p.Ecap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ws.ev_cnt; i += gridDim.x * blockDim.x) {
+  for (int i = part * blockDim.x + threadIdx.x; i < ws.ev_cnt; i += nparts * blockDim.x) {
     const float4 pt = slab[i];
     if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) continue;   // never inserted
     const unsigned long long key = pack_cell(cell_of(pt.x), cell_of(pt.y), cell_of(pt.z), gen);
@@ -228,16 +229,14 @@ __global__ void __launch_bounds__(256) k_hash_evict(DevBuffers d, int lane0) {
 }
 
 // New frame, pass 1: cell of every point (created if new), rank among the frame's points of that cell.
-__global__ void __launch_bounds__(256) k_hash_add_count(DevBuffers d, int lane0) {
-  const int lane_b = lane0 + blockIdx.y;
+__device__ __forceinline__ void hash_add_count_part(const DevBuffers& d, int lane_b, int part, int nparts) {
   WinState& ws = d.wstate[lane_b];
-  if (ws.hmode != kHashIncr) return;
   const unsigned gen = ws.gen & ((1u << kGenBits) - 1u);
   const unsigned mask = (unsigned)d.p.Hcap - 1u;
   HashEntry* tab = d.htab + (size_t)lane_b * d.p.Hcap;
   unsigned* newcnt = d.newcnt + (size_t)lane_b * d.p.Hcap;
   const float4* slab = d.win + ((size_t)lane_b * d.p.slots + ws.nw_slab) * d.p.Ecap;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ws.nw_cnt; i += gridDim.x * blockDim.x) {
+  for (int i = part * blockDim.x + threadIdx.x; i < ws.nw_cnt; i += nparts * blockDim.x) {
     const float4 pt = slab[i];
     unsigned* pslot = d.pt_slot + (size_t)lane_b * d.p.Mcap + i;
     if (!(isfinite(pt.x) && isfinite(pt.y) && isfinite(pt.z))) { *pslot = 0xffffffffu; continue; }
@@ -254,6 +253,14 @@ __global__ void __launch_bounds__(256) k_hash_add_count(DevBuffers d, int lane0)
     *pslot = slot;
     d.pt_rank[(size_t)lane_b * d.p.Mcap + i] = rank;
   }
+}
+
+__global__ void __launch_bounds__(256) k_hash_evict_add(DevBuffers d, int lane0) {
+  const int lane_b = lane0 + blockIdx.y;
+  if (d.wstate[lane_b].hmode != kHashIncr) return;
+  const int half = gridDim.x >> 1;   // the grid has an even number of CTAs per lane
+  if (blockIdx.x & 1) hash_add_count_part(d, lane_b, blockIdx.x >> 1, half);
+  else hash_evict_part(d, lane_b, blockIdx.x >> 1, half);
 }
 
 // New frame, pass 2: eight threads per touched cell make room at the tail of its bucket; a bucket that has reached
@@ -387,11 +394,10 @@ int launch_hash_build(const DevBuffers& d, cudaStream_t s, LaneRange lr) {
   }
   const dim3 ge((d.p.Ecap + 255) / 256, nlanes);
   k_hash_full_ordered<<<nlanes, kFullThreads, 0, s>>>(d, lane0);
-  k_hash_evict<<<ge, 256, 0, s>>>(d, lane0);
-  k_hash_add_count<<<ge, 256, 0, s>>>(d, lane0);
+  k_hash_evict_add<<<dim3(2 * ge.x, ge.y), 256, 0, s>>>(d, lane0);
   k_hash_grow<<<dim3((d.p.Ecap * kGrowGroup / 4 + 255) / 256, nlanes), 256, 0, s>>>(d, lane0);   // ~4 groups' worth of threads per possible cell pair; grid-stride
   k_hash_add_scatter<<<ge, 256, 0, s>>>(d, lane0);
-  return 5;
+  return 4;
 }
 
 // ---------------------------------------------------------------------------------------

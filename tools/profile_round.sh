@@ -8,7 +8,7 @@
 TAG=${1:-r02}
 LANES=${2:-128}
 export LIODOM_LANE_GROUPS=1
-PER=19                       # launches per step with one lane group (incremental hash: 5 build kernels)
+PER=18                       # launches per step with one lane group (incremental hash: 4 build kernels)
 PRE=$(( (16 + 3) * PER ))    # pre-roll 16 + warm-up 3 steps
 BENCH="python bench.py --lanes $LANES --steps 2 --warmup 3 --no-cpu-baseline --no-stage-pass --no-single-stream --no-sharded-block --no-xyz12"
 mkdir -p gpurun_out
