@@ -1044,21 +1044,23 @@ __global__ void __launch_bounds__(kAssocThreads, G == 1 ? LIODOM_ASSOC_MINB : 8)
 }
 
 // ---------------------------------------------------------------------------------------
-// Large batches: thread-per-edge search whose NEIGHBOUR-cell candidates are pooled over the warp.
+// Large batches: thread-per-edge set-up, candidates pooled over the warp (the default for the second outer iteration).
 //
-// Replay of the C1 data (tools/assoc_work_analysis.py --warp-sim): a warp of the thread-per-edge kernel spends 62
-// four-candidate iterations per 32 edges, 12 on the own cells and 50 on neighbour cells, although the 32 edges together
-// hold only 16 iterations' worth of candidates: neighbouring edges differ widely in how many neighbour points survive
-// their bound.  So the search is split:
-//   phase A  (as before, one thread per edge) own cell, then the neighbour cells nearest first — scanned in place while
-//            the edge has fewer than five candidates (no bound yet), LISTED (start, count) in shared memory once it has
-//            a bound; cells the bound excludes are skipped as before;
+// Replay of the C1 data (tools/assoc_warp_sim.py): a warp of the thread-per-edge kernel spends 62 four-candidate
+// iterations per 32 edges, 12 on the own cells and 50 on neighbour cells, although the 32 edges together hold only 16
+// iterations' worth of candidates: neighbouring edges differ widely in how many neighbour points survive their bound.
+// So the search is split:
+//   phase A  one thread per edge.  An edge with a bound in hand LISTS (start, count) in shared memory every cell the
+//            bound cannot exclude; an edge without one scans in place (own cell, then the neighbour cells nearest
+//            first) until it holds five candidates, and lists the rest.  In the second outer iteration the bound is
+//            there from the start — the largest distance to the five neighbours of the first iteration — so the own
+//            cell is listed too and nothing is scanned in place;
 //   phase B  the warp's listed buckets form one candidate sequence that is cut into 32 equal chunks; every lane scans
-//            one chunk on behalf of the owning edges (query and bound read from shared memory) and pushes the candidates
-//            that pass the owner's bound (3 per edge on average) onto the owner's list in a per-warp pool;
+//            one chunk on behalf of the owning edges (query and bound read from shared memory) and splices the
+//            candidates that pass the owner's bound (3 - 6 per edge) into the owner's list in a per-warp pool;
 //   phase C  every owner merges its list into its five best.
 // The candidate set an edge sees is a superset of the one the thread-per-edge kernel examines under its progressively
-// tightened bound, every rejected candidate is beyond the bound the edge already holds, and the five best of a set do
+// tightened bound, every rejected candidate is beyond a bound the edge already holds, and the five best of a set do
 // not depend on the order of insertion: results are bit-identical.  When the pool runs over, owners that lost a
 // candidate scan their listed buckets themselves.
 // ---------------------------------------------------------------------------------------
