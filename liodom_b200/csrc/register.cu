@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
   const int n = min(kOrderChunk, os.n_edges - base);
   if (n <= 0) return;
   extern __shared__ unsigned long long sk[];
-  int np2 = 32;
+  int np2 = 64;
   while (np2 < n) np2 <<= 1;
   const float4* edges = d.edges + (size_t)lane_b * p.Ecap + base;
   const float m0 = (float)os.odom[0], m1 = (float)os.odom[1], m2 = (float)os.odom[2], m3 = (float)os.odom[3];
@@ -572,18 +572,43 @@ __global__ void __launch_bounds__(1024) k_edge_order(DevBuffers d, int lane0) {
     sk[i] = v;
   }
   __syncthreads();
-  // Thread t owns the pairs t, t + 1024, ...; for j <= 32 both elements of all its pairs (and of its
-  // warp's pairs) stay inside the warp's own 64-element blocks, so those phases need only a warp sync.
-  for (int k = 2; k <= np2; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  // Bitonic sort (the keys are unique, so the result does not depend on the network).  Every warp owns 64-element
+  // blocks; all compare-exchanges at distance j <= 32 stay inside a block, so they run in registers — lane l holds
+  // elements l and l + 32 of the block: j = 32 pairs them inside the lane, j <= 16 is a shuffle — and only the
+  // distances >= 64 go through shared memory: 15 block-wide stages instead of 66 for 2048 keys.
+  const int ln = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  auto block_stages = [&](int k, bool from32) {   // the stages j = 32 (if from32) or min(k / 2, 16) ... 1 of merge size k
+    for (int b = wid; b < (np2 >> 6); b += nwarps) {
+      const int e0 = (b << 6) + ln, e1 = e0 + 32;
+      unsigned long long a = sk[e0], c = sk[e1];
+      if (from32) {
+        const bool asc = (e0 & k) == 0;
+        if ((a > c) == asc) { const unsigned long long t = a; a = c; c = t; }
+      }
+      const bool asc_a = (e0 & k) == 0, asc_c = (e1 & k) == 0;
+      for (int j = from32 ? 16 : min(k >> 1, 16); j > 0; j >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, j), oc = __shfl_xor_sync(0xffffffffu, c, j);
+        const bool lower = (ln & j) == 0;
+        a = ((lower == asc_a) == (a < oa)) ? a : oa;   // keep the smaller one in the lower position of an ascending pair
+        c = ((lower == asc_c) == (c < oc)) ? c : oc;
+      }
+      sk[e0] = a; sk[e1] = c;
+    }
+  };
+  for (int k = 2; k <= 32; k <<= 1) { block_stages(k, false); }   // (block-local: no barrier needed between them)
+  for (int k = 64; k <= np2; k <<= 1) {
+    __syncthreads();
+    for (int j = k >> 1; j >= 64; j >>= 1) {
       for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
         const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
         const unsigned long long a = sk[lo], b = sk[hi];
         const bool up = (lo & k) == 0;
         if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
       }
-      if (j > 32 || (j == 1 && k >= 64)) __syncthreads(); else __syncwarp();
+      __syncthreads();
     }
+    block_stages(k, true);
+  }
   __syncthreads();
   int* perm = d.perm + (size_t)lane_b * p.Ecap + base;
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = base + (int)(unsigned)(sk[i] & 0xffffffffull);

@@ -110,7 +110,7 @@ def test_batch128_warp_pooled_association(cuda_lib, pool, monkeypatch):
 def test_batch_other_baseline_shapes(cuda_lib, name):
     """The other BASELINE.json shapes through the batched path with a full window (the incremental voxel hash with
     21-frame / 128-ring windows): C2 = OS1-128 organised clouds, C3 = scan_regions / edges_per_region doubled and
-    prev_frames = 20.  8 lanes (4 seeds), every lane and frame against the oracle's free run."""
+    prev_frames = 20.  12 lanes (4 seeds), every lane and frame against the oracle's free run."""
     from liodom_b200 import synth
     if name == "c2_ouster":
         sensor, nfr = "os1_128", 18
@@ -125,11 +125,12 @@ def test_batch_other_baseline_shapes(cuda_lib, name):
     seqs = [get_sequence(sensor, sd, nfr)[0] for sd in seeds]
     op = oracle.make_params(**kw)
     oruns = [oracle.run_sequence(op, sq, w, h)[0] for sq in seqs]
-    ctx = api.Context(batch=8, max_points=maxp, **kw)
+    nl = 12   # enough edges in flight for the one-thread-per-edge kernels (k_associate<1> + k_associate_pool) at both shapes
+    ctx = api.Context(batch=nl, max_points=maxp, **kw)
     for f in range(nfr):
-        ctx.scan_batch([seqs[l % 4][f] for l in range(8)], width=w, height=h)
+        ctx.scan_batch([seqs[l % 4][f] for l in range(nl)], width=w, height=h)
         poses, ne = ctx.results()
-        for l in range(8):
+        for l in range(nl):
             dt, dr = pose_err(poses[l], oruns[l % 4][f])
             assert dt < TOL_T and dr < TOL_R, "%s lane %d frame %d: %g m, %g rad" % (name, l, f, dt, dr)
     ctx.close()
