@@ -440,7 +440,7 @@ __device__ int run_region_reg(const RingView& rv, const unsigned* gapbits, int w
 // than the shared-memory capacity (1M-point scans: 15,625 points per ring, one CTA per ring is all the parallelism
 // there is, so the CTA should be as wide as possible: 32 warps for the curvature and the 64 regions).
 template <int NT>
-__global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 1) k_extract(DevBuffers d, int lane0, int ring_cap, int want_keys, int ring0) {
   const DevParams& p = d.p;
   const int lane_b = lane0 + blockIdx.y, ring = ring0 + blockIdx.x;   // ring0 > 0: ring-sharded extraction
   const int L = p.scan_lines, R = p.scan_regions, epr = p.edges_per_region, E1 = epr + 1;
@@ -506,6 +506,34 @@ __global__ void __launch_bounds__(NT) k_extract(DevBuffers d, int lane0, int rin
   }
   // curvature
   double* gkeys = (want_keys && d.keys) ? d.keys + (size_t)lane_b * p.Ncap + off : nullptr;
+  if (in_smem) {
+    // Every thread takes runs of kRun CONSECUTIVE points and slides an 11-point window through registers: 10 + kRun
+    // shared-memory loads per run instead of 11 per point.  kRun = 9: the lanes' float4 reads are 144 bytes apart,
+    // which keeps a quarter-warp on distinct banks (a power-of-two run length would put all eight on the same four).
+    constexpr int kRun = 9;
+    for (int r0 = tid * kRun; r0 < n - 10; r0 += blockDim.x * kRun) {
+      const int j0 = 5 + r0;
+      float wx[11], wy[11], wz[11];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) { const float4 v = sp[j0 - 5 + k]; wx[k] = v.x; wy[k] = v.y; wz[k] = v.z; }
+#pragma unroll
+      for (int q = 0; q < kRun; ++q) {
+        const int j = j0 + q;
+        const float4 v = sp[min(j + 5, n - 1)];
+        wx[10] = v.x; wy[10] = v.y; wz[10] = v.z;
+        const double dx = (double)tap11(wx[0], wx[1], wx[2], wx[3], wx[4], wx[5], wx[6], wx[7], wx[8], wx[9], wx[10]);
+        const double dy = (double)tap11(wy[0], wy[1], wy[2], wy[3], wy[4], wy[5], wy[6], wy[7], wy[8], wy[9], wy[10]);
+        const double dz = (double)tap11(wz[0], wz[1], wz[2], wz[3], wz[4], wz[5], wz[6], wz[7], wz[8], wz[9], wz[10]);
+        const double key = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (j < n - 5) {
+          sk[j] = key;
+          if (gkeys) gkeys[j] = key;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { wx[k] = wx[k + 1]; wy[k] = wy[k + 1]; wz[k] = wz[k + 1]; }
+      }
+    }
+  } else
   for (int j = 5 + tid; j < n - 5; j += blockDim.x) {
     const float4 a0 = rv.P[j - 5], a1 = rv.P[j - 4], a2 = rv.P[j - 3], a3 = rv.P[j - 2], a4 = rv.P[j - 1];
     const float4 c = rv.P[j];
