@@ -106,24 +106,27 @@ __device__ __forceinline__ bool ring_of_point_fast(const DevParams& p, const Sca
   return true;
 }
 
-__device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, bool& amb) {
-  {
-    int fast_id;
-    if (ring_of_point_fast(p, sc, i, xf, yf, zf, &fast_id)) { amb = false; return fast_id; }
-  }
+// The reference's double arithmetic, for the points the FP32 screen cannot call.  Not inlined: the split kernels
+// unroll their point loop eight times, and eight copies of the FP64 sqrt / division / atan made k_split_count 5000
+// instructions long (instruction-cache misses: 3 warps per issue stalled on `no_instruction`).
+// (scalars by value: a reference to the parameter structs would force a local-memory copy of them in the caller)
+__device__ __noinline__ int ring_of_point_exact(double min_range, double max_range, int lidar_type, int scan_lines, int width, int i,
+                                                float xf, float yf, float zf, bool* amb_out) {
+  bool amb;
   const double x = xf, y = yf, z = zf;
   bool valid = isfinite(x) && isfinite(y) && isfinite(z);
   const double dist = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
-  if (dist > p.max_range || dist < p.min_range) valid = false;
+  if (dist > max_range || dist < min_range) valid = false;
   amb = false;
+  *amb_out = false;
   if (!valid) return -1;
-  if (p.lidar_type == 1) {
-    const int row = i / sc.width;
-    return row < p.scan_lines ? row : -1;
+  if (lidar_type == 1) {
+    const int row = i / width;
+    return row < scan_lines ? row : -1;
   }
   const double angle = __ddiv_rn(__dmul_rn(atan(__ddiv_rn(z, dist)), 180.0), 3.14159265358979323846);
   int id = -1;
-  if (p.scan_lines == 64) {
+  if (scan_lines == 64) {
     double v;
     if (angle >= -8.83) { v = __dadd_rn(__dmul_rn(__dsub_rn(2.0, angle), 3.0), 0.5); id = __double2int_rz(v); }
     else { v = __dadd_rn(__dmul_rn(__dsub_rn(-8.83, angle), 2.0), 0.5); id = 32 + __double2int_rz(v); }
@@ -134,16 +137,23 @@ __device__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, floa
       amb = amb || hi != lo;
     }
     if (angle > 2.0 || angle < -24.33 || id > 63 || id < 0) id = -1;
-  } else if (p.scan_lines == 32) {
+  } else if (scan_lines == 32) {
     const double v = __ddiv_rn(__dmul_rn(__dadd_rn(angle, 92.0 / 3.0), 3.0), 4.0);
     id = __double2int_rz(v); amb = near_int(v);
     if (id > 31 || id < 0) id = -1;
-  } else if (p.scan_lines == 16) {
+  } else if (scan_lines == 16) {
     const double v = __dadd_rn(__ddiv_rn(__dadd_rn(angle, 15.0), 2.0), 0.5);
     id = __double2int_rz(v); amb = near_int(v);
     if (id > 15 || id < 0) id = -1;
   }
+  *amb_out = amb;
   return id;
+}
+
+__device__ __forceinline__ int ring_of_point(const DevParams& p, const ScanDesc& sc, int i, float xf, float yf, float zf, bool& amb) {
+  int fast_id;
+  if (ring_of_point_fast(p, sc, i, xf, yf, zf, &fast_id)) { amb = false; return fast_id; }
+  return ring_of_point_exact(p.min_range, p.max_range, p.lidar_type, p.scan_lines, sc.width, i, xf, yf, zf, &amb);
 }
 
 // Pass 1: ring id per point + per-chunk histogram. grid (chunks, B), 256 threads, each warp
