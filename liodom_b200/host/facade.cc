@@ -673,19 +673,7 @@ double Map::getMapEntropy() {
 // src/liodom_mapping_node.cc:45-90): it feeds clouds through SharedData exactly like lidarClb does
 // and runs the two worker functors on their own threads.  C linkage so that tests can call it.
 // ---------------------------------------------------------------------------------------------
-extern "C" {
-
-struct liodom_host_options {
-  double min_range, max_range;
-  int lidar_type, scan_lines, scan_regions, edges_per_region, prev_frames, mapping;
-  int width, height;   // organised clouds (lidar_type 1)
-  int lockstep;        // 1: wait for each frame's pose before pushing the next cloud (deterministic)
-  int filter_local_map;
-};
-
-// scans: concatenated float32 x,y,z,intensity; npts[nframes]. poses_out: nframes x 16 (row-major).
-// Returns the number of poses produced, or a negative value on setup failure.
-}  // extern "C"
+#include <liodom/harness.h>   // liodom_host_options and the harness entry points defined below
 
 static std::vector<double> g_run_push_ms, g_run_pose_ms;   // liodom_host_last_run_times()
 

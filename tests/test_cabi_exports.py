@@ -25,6 +25,20 @@ def test_every_declared_symbol_is_exported():
     assert not missing, missing
 
 
+def test_harness_header_matches_the_host_library():
+    """include/liodom/harness.h: every declared entry point is exported by libliodom_host.so, and the header compiles as C."""
+    import subprocess
+    from liodom_b200 import build
+    so = build.build_host()
+    lib = ctypes.CDLL(so)
+    src = open(os.path.join(ROOT, "include", "liodom", "harness.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(liodom_host_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) == 5, names
+    assert not [n for n in names if not hasattr(lib, n)]
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "liodom", "harness.h")], check=True)
+
+
 def test_no_device_means_no_context():
     import torch
     if torch.cuda.is_available():
