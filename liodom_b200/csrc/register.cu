@@ -1520,6 +1520,8 @@ __global__ void __launch_bounds__(128) k_line_gate(DevBuffers d, int lane0, int 
 // Threads per edge: 1 for large batches (least total work); 4, 8 or 16 while the launch would otherwise leave most
 // of the 148 SMs idle (shorter per-edge chains; measured per lane count).  LIODOM_ASSOC_GROUP=1|4|8|16 forces a
 // variant (the parity tests cover all four).
+// (The variant switches are read per launch — a getenv is ~100 ns against launches of 100+ us — so that one process,
+// e.g. the parity tests, can run every variant.)
 static int assoc_group_size(long long edges_in_flight) {
   if (const char* e = getenv("LIODOM_ASSOC_GROUP")) { const int v = atoi(e); if (v == 1 || v == 4 || v == 8 || v == 16) return v; }
   if (edges_in_flight <= 5632) return 16;
