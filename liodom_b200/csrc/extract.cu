@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(kMaxLines) k_split_scan(DevBuffers d, int lane
 
 // Pass 3: stable scatter into ring-major order. grid (chunks, B), 256 threads.
 __global__ void __launch_bounds__(256) k_split_scatter(DevBuffers d, int lane0) {
-  const int lane_b = lane0 + blockIdx.y, chunk = blockIdx.x;
+  // CTAs walk the batch in the REVERSE of k_split_count's order: the scans that pass read last are still in L2
+  const int lane_b = lane0 + (int)(gridDim.y - 1u - blockIdx.y), chunk = (int)(gridDim.x - 1u - blockIdx.x);
   const ScanDesc sc = d.scan[lane_b];
   const DevParams& p = d.p;
   const int L = p.scan_lines;
